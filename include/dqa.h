@@ -1,0 +1,130 @@
+/* dqa.h -- C ABI of libdqa.so, the B200-native engine for the digitized-Quantum-Annealing
+ * MPS step of baronefr/perceptron-dqa.
+ *
+ * The reference has no FFI: its boundary is the Python class `mydQA` (dQA_mps.py:38-185)
+ * and the op-level functions of lib/tenn.py.  Each entry point below names the reference
+ * interface it stands behind; INTEGRATION.md shows the ctypes binding a maintainer adds to
+ * dQA_mps.py to switch the hot path over.
+ *
+ * Conventions
+ *  - C linkage, no exceptions, no C++/torch types.  Every function returns 0 on success,
+ *    a negative DQA_E* code for argument/state errors, a positive value = cudaError_t for
+ *    CUDA failures; dqa_last_error() gives the message.
+ *  - The caller owns all device memory: ask dqa_workspace_bytes(), allocate (e.g. a torch
+ *    uint8 tensor), hand the pointer to dqa_bind_workspace().  Nothing is allocated in
+ *    dqa_step().  Host buffers are caller-allocated.
+ *  - complex128 is interleaved (re, im) doubles, the numpy layout.  MPS site tensors cross
+ *    the ABI in the reference's (l, phys=2, r) row-major layout (lib/tenn.py:72-75).
+ *  - A handle is bound to one device and one stream and is not thread-safe; calls are
+ *    stream-ordered, the get/energy calls synchronise the stream.
+ *  - There is no CPU fallback anywhere behind this ABI.
+ */
+#ifndef DQA_H_
+#define DQA_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct dqa_handle dqa_t;
+
+enum {
+  DQA_OK = 0,
+  DQA_EINVAL = -1,   /* bad argument */
+  DQA_ESTATE = -2,   /* call order (workspace / patterns / tables not set) */
+  DQA_ELIMIT = -3,   /* size outside what the kernels support */
+  DQA_ENUMERIC = -4  /* some instance went non-finite / zero norm / Jacobi did not converge */
+};
+
+/* mydQA.__init__(dataset, P, dt, max_bond) (dQA_mps.py:40-60) plus the truncation policy
+ * hard-coded at lib/tenn.py:238 (cutoff=1e-10, cutoff_mode=4 'rsum2', renorm=2, absorb right),
+ * exposed as plan fields defaulting to those values, and the ensemble size. */
+typedef struct dqa_config {
+  int32_t N;           /* sites = pattern length                          */
+  int32_t n_xi;        /* patterns per realisation                        */
+  int32_t P;           /* annealing steps                                 */
+  int32_t chi;         /* max_bond                                        */
+  int32_t batch;       /* independent realisations evolved by this handle */
+  int32_t device;      /* CUDA device ordinal                             */
+  int32_t max_sweeps;  /* Jacobi sweep cap (0 -> 30)                      */
+  int32_t reserved;
+  double dt;
+  double cutoff;       /* 0 -> 1e-10 (lib/tenn.py:238); <0 -> no cutoff    */
+  void* stream;        /* cudaStream_t, NULL = legacy default stream      */
+} dqa_config;
+
+/* life cycle ---------------------------------------------------------------------- */
+int dqa_create(dqa_t** h, const dqa_config* cfg);
+void dqa_destroy(dqa_t* h);
+const char* dqa_last_error(const dqa_t* h);
+int dqa_workspace_bytes(const dqa_t* h, size_t* bytes);
+int dqa_bind_workspace(dqa_t* h, void* device_ptr, size_t bytes);
+
+/* inputs -------------------------------------------------------------------------- */
+/* xi: host int8 [batch][n_xi][N], every entry +-1 (self.dataset, dQA_mps.py:46-52). */
+int dqa_set_patterns(dqa_t* h, const int8_t* xi);
+/* Tables of mydQA.init_fourier (dQA_mps.py:62-66), computed by the caller exactly as the
+ * reference does: Uk_FT host complex128 [D][P], fxft host complex128 [D], D = N+1. */
+int dqa_set_fourier(dqa_t* h, const double* Uk_FT, const double* fxft);
+/* Integer pattern-to-MPO tables, computed ON THE DEVICE, for the bit-exact check
+ * (lib/dQA_utils.py:50-53,106): hbit [n_xi][N] u8, e [n_xi][N][2] i32, q [n_xi][N][2][D] i32.
+ * Any output pointer may be NULL. */
+int dqa_get_index_tensors(dqa_t* h, int inst, uint8_t* hbit, int32_t* e, int32_t* q);
+
+/* the driver path: mydQA.run / single_step (dQA_mps.py:84-174) ------------------------ */
+int dqa_reset_plus(dqa_t* h);            /* |+>^N, pp=0, eps[0] = eps(0)               */
+int dqa_step(dqa_t* h, int nsteps);      /* nsteps x single_step(); DQA_ENUMERIC if any
+                                            instance's status word is non-zero          */
+int dqa_get_step(const dqa_t* h, int* pp);
+int dqa_set_step(dqa_t* h, int pp);
+
+/* sub-steps, for teacher-forced parity ---------------------------- */
+/* U_z^mu at step p + right_canonize + compress_svd_normalized (dQA_mps.py:94-103). */
+int dqa_apply_pattern(dqa_t* h, int p, int mu);
+/* only the right-canonisation half (lib/tenn.py:179-190), leaving the sector factors in the
+ * workspace; dqa_truncate then runs the left-to-right truncation (lib/tenn.py:255-262). */
+int dqa_canonize(dqa_t* h, int p, int mu);
+int dqa_truncate(dqa_t* h, int p, int mu);
+/* make_Ux + apply_mpsmpo (lib/dQA_utils.py:26-30, dQA_mps.py:108-109). */
+int dqa_apply_ux(dqa_t* h, double beta);
+/* mydQA.compute_loss on the current state (dQA_mps.py:68-81): eps host complex128 [batch]. */
+int dqa_energy(dqa_t* h, double* eps);
+
+/* state access: checkpoint / resume / teacher forcing -------------------------------- */
+int dqa_get_bonds(dqa_t* h, int inst, int32_t* bonds /* [N+1] */);
+int dqa_get_mps(dqa_t* h, int inst, int site, double* buf /* l*2*r complex */, int* l, int* r);
+int dqa_set_mps(dqa_t* h, int inst, int site, const double* buf, int l, int r);
+/* singular values seen at cut `bond` (between sites bond and bond+1) by the last truncation. */
+int dqa_get_schmidt(dqa_t* h, int inst, int bond, double* s /* [2*chi] */, int* n);
+
+/* traces: self.loss / self.bd_monitor (dQA_mps.py:105-106,116,147) ------------------- */
+int dqa_get_eps(dqa_t* h, double* eps /* [batch][P+1] complex */);
+int dqa_get_bd_monitor(dqa_t* h, int32_t* bd /* [batch][P*n_xi] */);
+int dqa_get_status(dqa_t* h, int32_t* status /* [batch] */);
+/* [batch][4] u64: Jacobi rotations, Jacobi sweeps, SVDs, QR columns (for the FLOP count). */
+int dqa_get_counters(dqa_t* h, uint64_t* counters, int reset);
+
+/* ensemble moments for the multi-GPU reduction: writes to DEVICE memory (caller-owned,
+ * 3*(P+1) doubles): sum_r Re eps_r(s), sum_r (Re eps_r(s))^2, number of healthy instances;
+ * the caller all-reduces that buffer (one ncclAllReduce of 24 KB at P=1000). */
+int dqa_ensemble_moments(dqa_t* h, double* device_out);
+
+/* profiling: per kernel-family device time, measured with CUDA events on the handle's
+ * stream.  families: 0 sector_qr, 1 theta, 2 svd, 3 mixer, 4 energy. */
+#define DQA_NFAM 5
+int dqa_profile_begin(dqa_t* h);
+int dqa_profile_end(dqa_t* h, double* ms /* [DQA_NFAM] */, int64_t* launches /* [DQA_NFAM] */);
+
+/* FP64 FMA throughput of this device (TFLOP/s), measured by a register-resident DFMA loop;
+ * the roofline denominator for the FP64-bound kernels (MEASURED_PEAKS.json has no FP64 entry). */
+int dqa_measure_fp64_peak(dqa_t* h, double* tflops);
+
+const char* dqa_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DQA_H_ */

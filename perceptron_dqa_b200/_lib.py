@@ -1,0 +1,269 @@
+"""ctypes binding of libdqa.so (include/dqa.h).
+
+The product path is CUDA only: `load()` raises if the nvcc-built library is missing -- there
+is no CPU fallback.  `Plan` is a thin object wrapper over one `dqa_t*`; PyTorch is used for
+exactly one thing, owning the device workspace (a uint8 tensor) and naming the stream.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdqa.so")
+NFAM = 5
+FAMILIES = ("sector_qr", "theta", "svd", "mixer", "energy")
+
+
+class DqaError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"libdqa error {code}: {msg}")
+        self.code = code
+
+
+class DqaNumericError(DqaError):
+    """Some instance went non-finite / lost its norm / Jacobi did not converge (DQA_ENUMERIC)."""
+
+
+class dqa_config(C.Structure):
+    _fields_ = [
+        ("N", C.c_int32), ("n_xi", C.c_int32), ("P", C.c_int32), ("chi", C.c_int32),
+        ("batch", C.c_int32), ("device", C.c_int32), ("max_sweeps", C.c_int32), ("reserved", C.c_int32),
+        ("dt", C.c_double), ("cutoff", C.c_double), ("stream", C.c_void_p),
+    ]
+
+
+_P = C.c_void_p
+_SIGS = {
+    "dqa_create": ([C.POINTER(_P), C.POINTER(dqa_config)], C.c_int),
+    "dqa_destroy": ([_P], None),
+    "dqa_last_error": ([_P], C.c_char_p),
+    "dqa_workspace_bytes": ([_P, C.POINTER(C.c_size_t)], C.c_int),
+    "dqa_bind_workspace": ([_P, _P, C.c_size_t], C.c_int),
+    "dqa_set_patterns": ([_P, _P], C.c_int),
+    "dqa_set_fourier": ([_P, _P, _P], C.c_int),
+    "dqa_get_index_tensors": ([_P, C.c_int, _P, _P, _P], C.c_int),
+    "dqa_reset_plus": ([_P], C.c_int),
+    "dqa_step": ([_P, C.c_int], C.c_int),
+    "dqa_get_step": ([_P, C.POINTER(C.c_int)], C.c_int),
+    "dqa_set_step": ([_P, C.c_int], C.c_int),
+    "dqa_apply_pattern": ([_P, C.c_int, C.c_int], C.c_int),
+    "dqa_canonize": ([_P, C.c_int, C.c_int], C.c_int),
+    "dqa_truncate": ([_P, C.c_int, C.c_int], C.c_int),
+    "dqa_apply_ux": ([_P, C.c_double], C.c_int),
+    "dqa_energy": ([_P, _P], C.c_int),
+    "dqa_get_bonds": ([_P, C.c_int, _P], C.c_int),
+    "dqa_get_mps": ([_P, C.c_int, C.c_int, _P, C.POINTER(C.c_int), C.POINTER(C.c_int)], C.c_int),
+    "dqa_set_mps": ([_P, C.c_int, C.c_int, _P, C.c_int, C.c_int], C.c_int),
+    "dqa_get_schmidt": ([_P, C.c_int, C.c_int, _P, C.POINTER(C.c_int)], C.c_int),
+    "dqa_get_eps": ([_P, _P], C.c_int),
+    "dqa_get_bd_monitor": ([_P, _P], C.c_int),
+    "dqa_get_status": ([_P, _P], C.c_int),
+    "dqa_get_counters": ([_P, _P, C.c_int], C.c_int),
+    "dqa_ensemble_moments": ([_P, _P], C.c_int),
+    "dqa_profile_begin": ([_P], C.c_int),
+    "dqa_profile_end": ([_P, _P, _P], C.c_int),
+    "dqa_measure_fp64_peak": ([_P, C.POINTER(C.c_double)], C.c_int),
+    "dqa_version": ([], C.c_char_p),
+}
+EXPORTS = tuple(_SIGS)
+
+
+def declare(lib):
+    for name, (args, res) in _SIGS.items():
+        fn = getattr(lib, name)
+        fn.argtypes = args
+        fn.restype = res
+    return lib
+
+
+_lib = None
+
+
+def load():
+    """Load the CUDA library.  Fails loudly when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.isfile(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc, sm_100a).  There is no CPU fallback for the dQA hot path.")
+        _lib = declare(C.CDLL(LIB_PATH))
+    return _lib
+
+
+def _ptr(a):
+    return a.ctypes.data_as(_P)
+
+
+def _torch_workspace(nbytes, device):
+    import torch
+
+    if not torch.cuda.is_available():
+        raise RuntimeError("no CUDA device: the dQA hot path runs on the GPU only")
+    t = torch.empty(nbytes + 256, dtype=torch.uint8, device=f"cuda:{device}")
+    off = (-t.data_ptr()) % 256
+    return t, t.data_ptr() + off
+
+
+class Plan:
+    """One dqa_t*: N sites, n_xi patterns, P steps, bond chi, `batch` realisations on one GPU."""
+
+    def __init__(self, N, n_xi, P, dt, chi, batch=1, device=0, cutoff=0.0, max_sweeps=0, stream=None,
+                 lib=None, workspace=None):
+        self.lib = lib or load()
+        self.N, self.n_xi, self.P, self.dt, self.chi, self.batch, self.device = N, n_xi, P, dt, chi, batch, device
+        self.D = N + 1
+        cfg = dqa_config(N=N, n_xi=n_xi, P=P, chi=chi, batch=batch, device=device, max_sweeps=max_sweeps,
+                         reserved=0, dt=dt, cutoff=cutoff, stream=stream)
+        self._h = _P()
+        rc = self.lib.dqa_create(C.byref(self._h), C.byref(cfg))
+        if rc != 0:
+            msg = self.lib.dqa_last_error(self._h).decode() if self._h else "dqa_create failed"
+            if self._h:
+                self.lib.dqa_destroy(self._h)
+                self._h = None
+            raise DqaError(rc, msg)
+        nbytes = C.c_size_t()
+        self._ck(self.lib.dqa_workspace_bytes(self._h, C.byref(nbytes)))
+        self.workspace_bytes = nbytes.value
+        alloc = workspace or _torch_workspace
+        self._ws_owner, ptr = alloc(self.workspace_bytes, device)
+        self._ck(self.lib.dqa_bind_workspace(self._h, ptr, self.workspace_bytes))
+
+    def _ck(self, rc):
+        if rc != 0:
+            msg = self.lib.dqa_last_error(self._h).decode()
+            raise (DqaNumericError if rc == -4 else DqaError)(rc, msg)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.dqa_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # inputs --------------------------------------------------------------------------
+    def set_patterns(self, xi):
+        xi = np.ascontiguousarray(xi, dtype=np.int8).reshape(self.batch, self.n_xi, self.N)
+        self._ck(self.lib.dqa_set_patterns(self._h, _ptr(xi)))
+
+    def set_fourier(self, uk_ft, fxft):
+        uk = np.ascontiguousarray(uk_ft, dtype=np.complex128)
+        fx = np.ascontiguousarray(fxft, dtype=np.complex128)
+        assert uk.shape == (self.D, self.P) and fx.shape == (self.D,)
+        self._ck(self.lib.dqa_set_fourier(self._h, _ptr(uk), _ptr(fx)))
+
+    def index_tensors(self, inst=0):
+        hbit = np.empty((self.n_xi, self.N), dtype=np.uint8)
+        e = np.empty((self.n_xi, self.N, 2), dtype=np.int32)
+        q = np.empty((self.n_xi, self.N, 2, self.D), dtype=np.int32)
+        self._ck(self.lib.dqa_get_index_tensors(self._h, inst, _ptr(hbit), _ptr(e), _ptr(q)))
+        return hbit, e, q
+
+    # driver path -----------------------------------------------------------------------
+    def reset_plus(self):
+        self._ck(self.lib.dqa_reset_plus(self._h))
+
+    def step(self, nsteps=1):
+        self._ck(self.lib.dqa_step(self._h, nsteps))
+
+    @property
+    def pp(self):
+        v = C.c_int()
+        self._ck(self.lib.dqa_get_step(self._h, C.byref(v)))
+        return v.value
+
+    @pp.setter
+    def pp(self, v):
+        self._ck(self.lib.dqa_set_step(self._h, int(v)))
+
+    # sub-steps ---------------------------------------------------------------------------
+    def apply_pattern(self, p, mu):
+        self._ck(self.lib.dqa_apply_pattern(self._h, p, mu))
+
+    def canonize(self, p, mu):
+        self._ck(self.lib.dqa_canonize(self._h, p, mu))
+
+    def truncate(self, p, mu):
+        self._ck(self.lib.dqa_truncate(self._h, p, mu))
+
+    def apply_ux(self, beta):
+        self._ck(self.lib.dqa_apply_ux(self._h, float(beta)))
+
+    def energy(self):
+        out = np.empty(self.batch, dtype=np.complex128)
+        self._ck(self.lib.dqa_energy(self._h, _ptr(out)))
+        return out
+
+    # state -------------------------------------------------------------------------------
+    def bonds(self, inst=0):
+        b = np.empty(self.N + 1, dtype=np.int32)
+        self._ck(self.lib.dqa_get_bonds(self._h, inst, _ptr(b)))
+        return b
+
+    def get_mps(self, inst=0):
+        out = []
+        buf = np.empty(2 * self.chi * self.chi, dtype=np.complex128)
+        l, r = C.c_int(), C.c_int()
+        for site in range(self.N):
+            self._ck(self.lib.dqa_get_mps(self._h, inst, site, _ptr(buf), C.byref(l), C.byref(r)))
+            out.append(buf[: l.value * 2 * r.value].reshape(l.value, 2, r.value).copy())
+        return out
+
+    def set_mps(self, mps, inst=0):
+        assert len(mps) == self.N
+        for site, t in enumerate(mps):
+            t = np.ascontiguousarray(t, dtype=np.complex128)
+            assert t.ndim == 3 and t.shape[1] == 2
+            self._ck(self.lib.dqa_set_mps(self._h, inst, site, _ptr(t), t.shape[0], t.shape[2]))
+
+    def schmidt(self, bond, inst=0):
+        s = np.empty(2 * self.chi, dtype=np.float64)
+        n = C.c_int()
+        self._ck(self.lib.dqa_get_schmidt(self._h, inst, bond, _ptr(s), C.byref(n)))
+        return s[: n.value].copy()
+
+    # traces ------------------------------------------------------------------------------
+    def eps_trace(self):
+        out = np.empty((self.batch, self.P + 1), dtype=np.complex128)
+        self._ck(self.lib.dqa_get_eps(self._h, _ptr(out)))
+        return out
+
+    def bd_monitor(self):
+        out = np.empty((self.batch, self.P * self.n_xi), dtype=np.int32)
+        self._ck(self.lib.dqa_get_bd_monitor(self._h, _ptr(out)))
+        return out
+
+    def status(self):
+        out = np.empty(self.batch, dtype=np.int32)
+        self._ck(self.lib.dqa_get_status(self._h, _ptr(out)))
+        return out
+
+    def counters(self, reset=False):
+        out = np.empty((self.batch, 4), dtype=np.uint64)
+        self._ck(self.lib.dqa_get_counters(self._h, _ptr(out), int(reset)))
+        return out
+
+    def ensemble_moments_into(self, device_ptr):
+        self._ck(self.lib.dqa_ensemble_moments(self._h, device_ptr))
+
+    def profile_begin(self):
+        self._ck(self.lib.dqa_profile_begin(self._h))
+
+    def profile_end(self):
+        ms = np.zeros(NFAM, dtype=np.float64)
+        n = np.zeros(NFAM, dtype=np.int64)
+        self._ck(self.lib.dqa_profile_end(self._h, _ptr(ms), _ptr(n)))
+        return dict(zip(FAMILIES, ms.tolist())), dict(zip(FAMILIES, n.tolist()))
+
+    def fp64_peak_tflops(self):
+        v = C.c_double()
+        self._ck(self.lib.dqa_measure_fp64_peak(self._h, C.byref(v)))
+        return v.value

@@ -1,0 +1,605 @@
+// dqa_abi.cu -- the C ABI of libdqa.so (include/dqa.h): plan, workspace carving, launch order.
+// Host code only orchestrates; every arithmetic step of the hot path is a kernel in
+// dqa_kernels.cuh.  There is no CPU fallback: with no CUDA device every call that touches
+// the device returns the cudaError_t it got.
+#include "../../include/dqa.h"
+#include "dqa_kernels.cuh"
+
+#include <cmath>
+#include <complex>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+struct dqa_handle {
+  dqa_config cfg;
+  DqaDev dev;
+  cudaStream_t stream;
+  void* ws;
+  size_t ws_bytes;
+  int8_t* d_xi;   // [batch][n_xi][N]
+  int32_t* d_e;   // scratch for dqa_get_index_tensors
+  int32_t* d_q;
+  int pp;
+  bool have_patterns, have_fourier, have_state;
+  int t_qr, t_theta, t_svd, t_energy;  // block sizes
+  char err[512];
+  // profiling
+  bool profiling;
+  struct Ev { int fam; cudaEvent_t a, b; };
+  std::vector<Ev> evs;
+  size_t ev_used;
+};
+
+static int fail(const dqa_t* h, int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(const_cast<dqa_t*>(h)->err, sizeof(h->err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+#define CK(call)                                                                                         \
+  do {                                                                                                   \
+    cudaError_t e_ = (call);                                                                             \
+    if (e_ != cudaSuccess) return fail(h, (int)e_, "%s failed: %s", #call, cudaGetErrorString(e_)); \
+  } while (0)
+
+static size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
+
+// one table drives both the size query and the carving
+struct Carve {
+  char* base;
+  size_t off;
+  template <class T>
+  T* take(size_t n) {
+    T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+    off = align_up(off + n * sizeof(T));
+    return p;
+  }
+};
+
+struct Aux {
+  int8_t* d_xi;
+  int32_t* d_e;
+  int32_t* d_q;
+};
+
+static void carve(const dqa_config& c, DqaDev& d, Aux& aux, char* base, size_t* total) {
+  const size_t B = c.batch, N = c.N, D = c.N + 1, chi = c.chi, P = c.P, nx = c.n_xi;
+  Carve cv{base, 0};
+  d.mps = cv.take<cplx>(B * N * 2 * chi * chi);
+  d.bond = cv.take<int>(B * (N + 1));
+  d.hbit = cv.take<uint8_t>(B * nx * N);
+  d.uz = cv.take<cplx>(P * D);
+  d.gk = cv.take<cplx>(D);
+  d.phase = cv.take<cplx>(D);
+  d.rbuf = cv.take<cplx>(B * 2 * d.smax * chi * chi);
+  d.qbuf = cv.take<cplx>(B * (size_t)d.nsec_total * 2 * chi * chi);
+  d.qdim = cv.take<int>(B * (N + 1) * d.smax);
+  d.theta = cv.take<cplx>(B * 2 * 2 * chi * (size_t)d.ld_theta);
+  d.work = cv.take<cplx>(B * 2 * chi * (size_t)d.ld_theta);
+  d.scale = cv.take<double>(B);
+  d.schmidt = cv.take<double>(B * N * 2 * chi);
+  d.nsv = cv.take<int>(B * N);
+  d.tmk = cv.take<cplx>(B * nx * d.kh);
+  d.eps = cv.take<cplx>(B * (P + 1));
+  d.bdmon = cv.take<int>(B * P * nx);
+  d.status = cv.take<int>(B);
+  d.counters = cv.take<unsigned long long>(B * 4);
+  aux.d_xi = cv.take<int8_t>(B * nx * N);
+  aux.d_e = cv.take<int32_t>(nx * N * 2);
+  aux.d_q = cv.take<int32_t>(nx * N * 2 * D);
+  *total = cv.off;
+}
+
+extern "C" const char* dqa_version(void) { return "dqa-b200 0.1 (sector path, complex128)"; }
+
+extern "C" int dqa_create(dqa_t** out, const dqa_config* cfg) {
+  if (!out || !cfg) return DQA_EINVAL;
+  *out = nullptr;
+  dqa_t* h = new dqa_t();
+  h->err[0] = 0;
+  h->cfg = *cfg;
+  dqa_config& c = h->cfg;
+  if (c.max_sweeps <= 0) c.max_sweeps = 30;
+  if (c.cutoff == 0.0) c.cutoff = 1e-10;
+  if (c.cutoff < 0.0) c.cutoff = 0.0;
+  *out = h;  // returned even on error so the message can be read; caller destroys it
+  if (c.N < 2 || c.n_xi < 1 || c.P < 1 || c.chi < 1 || c.batch < 1) return fail(h, DQA_EINVAL, "N>=2, n_xi>=1, P>=1, chi>=1, batch>=1 required");
+  if (c.N > 254) return fail(h, DQA_ELIMIT, "N=%d > 254 not supported", c.N);
+  if (sector_qr_smem(c.chi) > 227 * 1024 || svd_smem(c.chi) > 227 * 1024 || energy_smem(c.chi) > 227 * 1024)
+    return fail(h, DQA_ELIMIT, "chi=%d needs more than 227 KB of shared memory per CTA in this build (max chi 48)", c.chi);
+  h->stream = (cudaStream_t)c.stream;
+  h->ws = nullptr;
+  h->ws_bytes = 0;
+  h->pp = 0;
+  h->have_patterns = h->have_fourier = h->have_state = false;
+  h->profiling = false;
+  h->ev_used = 0;
+  DqaDev& d = h->dev;
+  memset(&d, 0, sizeof(d));
+  d.N = c.N;
+  d.D = c.N + 1;
+  d.n_xi = c.n_xi;
+  d.chi = c.chi;
+  d.batch = c.batch;
+  d.P = c.P;
+  d.smax = c.N + 1;
+  d.ld_theta = ((c.chi * (c.N + 1)) + 1) & ~1;
+  d.nsec_total = dqa_secbase(c.N, c.N);
+  d.kh = d.D / 2 + 1;
+  d.max_sweeps = c.max_sweeps;
+  d.cutoff = c.cutoff;
+  // block sizes: warps scale with chi; the emulator build keeps them small
+#ifdef DQA_EMUL
+  h->t_qr = 64; h->t_theta = 64; h->t_svd = 64; h->t_energy = 64;
+#else
+  h->t_qr = c.chi <= 8 ? 128 : 256;
+  h->t_theta = 256;
+  h->t_svd = c.chi <= 4 ? 128 : (c.chi <= 8 ? 256 : (c.chi <= 16 ? 512 : 1024));
+  h->t_energy = c.chi <= 8 ? 64 : 256;
+#endif
+  CK(cudaSetDevice(c.device));
+  CK(cudaFuncSetAttribute(k_sector_qr, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sector_qr_smem(c.chi)));
+  CK(cudaFuncSetAttribute(k_svd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)svd_smem(c.chi)));
+  CK(cudaFuncSetAttribute(k_energy, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)energy_smem(c.chi)));
+  CK(cudaFuncSetAttribute(k_theta, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(cplx) * c.chi * c.chi)));
+  return DQA_OK;
+}
+
+extern "C" void dqa_destroy(dqa_t* h) {
+  if (!h) return;
+  for (auto& e : h->evs) {
+    cudaEventDestroy(e.a);
+    cudaEventDestroy(e.b);
+  }
+  delete h;
+}
+
+extern "C" const char* dqa_last_error(const dqa_t* h) { return h ? h->err : "null handle"; }
+
+extern "C" int dqa_workspace_bytes(const dqa_t* h, size_t* bytes) {
+  if (!h || !bytes) return DQA_EINVAL;
+  DqaDev tmp = h->dev;  // carve() only writes pointers; work on a copy
+  Aux aux;
+  carve(h->cfg, tmp, aux, nullptr, bytes);
+  return DQA_OK;
+}
+
+extern "C" int dqa_bind_workspace(dqa_t* h, void* p, size_t bytes) {
+  if (!h || !p) return DQA_EINVAL;
+  size_t need = 0;
+  DqaDev tmp = h->dev;
+  Aux aux;
+  carve(h->cfg, tmp, aux, nullptr, &need);
+  if (bytes < need) return fail(h, DQA_EINVAL, "workspace too small: %zu < %zu", bytes, need);
+  if ((uintptr_t)p & 255) return fail(h, DQA_EINVAL, "workspace must be 256-byte aligned");
+  carve(h->cfg, h->dev, aux, (char*)p, &need);
+  h->d_xi = aux.d_xi;
+  h->d_e = aux.d_e;
+  h->d_q = aux.d_q;
+  h->ws = p;
+  h->ws_bytes = bytes;
+  CK(cudaMemsetAsync(p, 0, need, h->stream));
+  h->have_patterns = h->have_fourier = h->have_state = false;
+  return DQA_OK;
+}
+
+#define NEED_WS() \
+  if (!h) return DQA_EINVAL; \
+  if (!h->ws) return fail(h, DQA_ESTATE, "bind a workspace first")
+
+extern "C" int dqa_set_patterns(dqa_t* h, const int8_t* xi) {
+  NEED_WS();
+  if (!xi) return DQA_EINVAL;
+  const size_t n = (size_t)h->cfg.batch * h->cfg.n_xi * h->cfg.N;
+  for (size_t i = 0; i < n; ++i)
+    if (xi[i] != 1 && xi[i] != -1) return fail(h, DQA_EINVAL, "pattern entry %zu is %d, not +-1", i, (int)xi[i]);
+  CK(cudaMemcpyAsync(h->d_xi, xi, n, cudaMemcpyHostToDevice, h->stream));
+  const int blocks = (int)((n + 255) / 256);
+  DQA_LAUNCH(k_hamming_tables, dim3(blocks < 1024 ? blocks : 1024), dim3(256), 0, h->stream, (const int8_t*)h->d_xi, (int)n,
+             h->dev.D, const_cast<uint8_t*>(h->dev.hbit), (int32_t*)nullptr, (int32_t*)nullptr);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(h->stream));
+  h->have_patterns = true;
+  return DQA_OK;
+}
+
+extern "C" int dqa_get_index_tensors(dqa_t* h, int inst, uint8_t* hbit, int32_t* e, int32_t* q) {
+  NEED_WS();
+  if (!h->have_patterns) return fail(h, DQA_ESTATE, "set patterns first");
+  if (inst < 0 || inst >= h->cfg.batch) return fail(h, DQA_EINVAL, "instance out of range");
+  const size_t n = (size_t)h->cfg.n_xi * h->cfg.N;
+  const int D = h->dev.D;
+  const int8_t* xi = h->d_xi + (size_t)inst * n;
+  const int blocks = (int)((n + 127) / 128);
+  // hbit is recomputed into the tail of d_q's scratch? no: reuse the plan's table for this instance
+  DQA_LAUNCH(k_hamming_tables, dim3(blocks), dim3(128), 0, h->stream, xi, (int)n, D, (uint8_t*)nullptr, h->d_e, h->d_q);
+  CK(cudaGetLastError());
+  if (hbit) CK(cudaMemcpyAsync(hbit, h->dev.hbit + (size_t)inst * n, n, cudaMemcpyDeviceToHost, h->stream));
+  if (e) CK(cudaMemcpyAsync(e, h->d_e, n * 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+  if (q) CK(cudaMemcpyAsync(q, h->d_q, n * 2 * D * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return DQA_OK;
+}
+
+extern "C" int dqa_set_fourier(dqa_t* h, const double* uk_ft, const double* fxft) {
+  NEED_WS();
+  if (!uk_ft || !fxft) return DQA_EINVAL;
+  typedef std::complex<double> cd;
+  const int D = h->dev.D, P = h->cfg.P;
+  const cd* uk = reinterpret_cast<const cd*>(uk_ft);
+  const cd* fx = reinterpret_cast<const cd*>(fxft);
+  // u_p(x) = (1/sqrt D) sum_k Uk_FT[k,p] exp(2 pi i k x / D): the diagonal of the Fourier MPO
+  // U_z (lib/dQA_utils.py:46-59, product over the N sites of the per-site coefficient and phases).
+  std::vector<cd> w(D), uz((size_t)P * D), gk(D), ph(D);
+  for (int k = 0; k < D; ++k) {
+    const double ang = 2.0 * M_PI * k / D;
+    w[k] = cd(std::cos(ang), std::sin(ang));
+    // phase table of the energy sweep: exp(i*(pi/D)*k*e) with e = 2 (lib/dQA_utils.py:106)
+    const double a2 = (M_PI / D) * k * 2.0;
+    ph[k] = cd(std::cos(a2), std::sin(a2));
+    gk[k] = fx[k] / std::sqrt((double)D);
+  }
+  const double rs = 1.0 / std::sqrt((double)D);
+  for (int p = 0; p < P; ++p)
+    for (int x = 0; x < D; ++x) {
+      cd acc(0.0, 0.0);
+      for (int k = 0; k < D; ++k) acc += uk[(size_t)k * P + p] * w[(int)(((long)k * x) % D)];
+      uz[(size_t)p * D + x] = acc * rs;
+    }
+  CK(cudaMemcpyAsync(const_cast<cplx*>(h->dev.uz), uz.data(), sizeof(cd) * uz.size(), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(const_cast<cplx*>(h->dev.gk), gk.data(), sizeof(cd) * D, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(const_cast<cplx*>(h->dev.phase), ph.data(), sizeof(cd) * D, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  h->have_fourier = true;
+  return DQA_OK;
+}
+
+// ---- profiling helpers ---------------------------------------------------------------
+static void prof_a(dqa_t* h, int fam) {
+  if (!h->profiling) return;
+  if (h->ev_used == h->evs.size()) {
+    dqa_handle::Ev e;
+    e.fam = fam;
+    cudaEventCreate(&e.a);
+    cudaEventCreate(&e.b);
+    h->evs.push_back(e);
+  }
+  h->evs[h->ev_used].fam = fam;
+  cudaEventRecord(h->evs[h->ev_used].a, h->stream);
+}
+static void prof_b(dqa_t* h) {
+  if (!h->profiling) return;
+  cudaEventRecord(h->evs[h->ev_used].b, h->stream);
+  h->ev_used++;
+}
+
+extern "C" int dqa_profile_begin(dqa_t* h) {
+  if (!h) return DQA_EINVAL;
+  h->profiling = true;
+  h->ev_used = 0;
+  return DQA_OK;
+}
+
+extern "C" int dqa_profile_end(dqa_t* h, double* ms, int64_t* launches) {
+  if (!h || !ms || !launches) return DQA_EINVAL;
+  CK(cudaStreamSynchronize(h->stream));
+  for (int f = 0; f < DQA_NFAM; ++f) ms[f] = 0.0, launches[f] = 0;
+  for (size_t i = 0; i < h->ev_used; ++i) {
+    float t = 0.f;
+    CK(cudaEventElapsedTime(&t, h->evs[i].a, h->evs[i].b));
+    ms[h->evs[i].fam] += t;
+    launches[h->evs[i].fam]++;
+  }
+  h->profiling = false;
+  h->ev_used = 0;
+  return DQA_OK;
+}
+
+// ---- launch sequences ------------------------------------------------------------------
+static int launch_canonize(dqa_t* h, int mu) {
+  const DqaDev& d = h->dev;
+  DQA_LAUNCH(k_sector_init, dim3(d.batch), dim3(32), 0, h->stream, d);
+  for (int n = d.N - 1; n >= 1; --n) {
+    prof_a(h, 0);
+    DQA_LAUNCH(k_sector_qr, dim3(d.N - n + 1, d.batch), dim3(h->t_qr), sector_qr_smem(d.chi), h->stream, d, n, mu);
+    prof_b(h);
+  }
+  CK(cudaGetLastError());
+  return DQA_OK;
+}
+
+static int launch_truncate(dqa_t* h, int p, int mu) {
+  const DqaDev& d = h->dev;
+  prof_a(h, 1);
+  DQA_LAUNCH(k_theta0, dim3(d.N, d.batch), dim3(64), 0, h->stream, d, mu, p);
+  prof_b(h);
+  for (int l = 0; l < d.N; ++l) {
+    if (l > 0) {
+      prof_a(h, 1);
+      DQA_LAUNCH(k_theta, dim3(d.N - l + 1, d.batch), dim3(h->t_theta), sizeof(cplx) * d.chi * d.chi, h->stream, d, l, mu);
+      prof_b(h);
+    }
+    prof_a(h, 2);
+    DQA_LAUNCH(k_svd, dim3(d.batch), dim3(h->t_svd), svd_smem(d.chi), h->stream, d, l, mu, p);
+    prof_b(h);
+  }
+  CK(cudaGetLastError());
+  return DQA_OK;
+}
+
+static int launch_energy(dqa_t* h, int slot) {
+  const DqaDev& d = h->dev;
+  prof_a(h, 4);
+  DQA_LAUNCH(k_energy, dim3(d.kh, d.n_xi, d.batch), dim3(h->t_energy), energy_smem(d.chi), h->stream, d);
+  DQA_LAUNCH(k_energy_reduce, dim3(d.batch), dim3(32), 0, h->stream, d, slot);
+  prof_b(h);
+  CK(cudaGetLastError());
+  return DQA_OK;
+}
+
+#define NEED_READY() \
+  NEED_WS(); \
+  if (!h->have_patterns || !h->have_fourier) return fail(h, DQA_ESTATE, "set patterns and Fourier tables first"); \
+  if (!h->have_state) return fail(h, DQA_ESTATE, "no state: call dqa_reset_plus or dqa_set_mps first")
+
+extern "C" int dqa_reset_plus(dqa_t* h) {
+  NEED_WS();
+  if (!h->have_patterns || !h->have_fourier) return fail(h, DQA_ESTATE, "set patterns and Fourier tables first");
+  const DqaDev& d = h->dev;
+  DQA_LAUNCH(k_init_plus, dim3(d.batch), dim3(256), 0, h->stream, d);
+  CK(cudaMemsetAsync(d.counters, 0, sizeof(unsigned long long) * 4 * d.batch, h->stream));
+  h->pp = 0;
+  h->have_state = true;
+  return launch_energy(h, 0);
+}
+
+extern "C" int dqa_get_step(const dqa_t* h, int* pp) {
+  if (!h || !pp) return DQA_EINVAL;
+  *pp = h->pp;
+  return DQA_OK;
+}
+extern "C" int dqa_set_step(dqa_t* h, int pp) {
+  if (!h) return DQA_EINVAL;
+  if (pp < 0 || pp > h->cfg.P) return fail(h, DQA_EINVAL, "step out of range");
+  h->pp = pp;
+  return DQA_OK;
+}
+
+extern "C" int dqa_canonize(dqa_t* h, int p, int mu) {
+  NEED_READY();
+  if (p < 0 || p >= h->cfg.P || mu < 0 || mu >= h->cfg.n_xi) return fail(h, DQA_EINVAL, "p or mu out of range");
+  return launch_canonize(h, mu);
+}
+extern "C" int dqa_truncate(dqa_t* h, int p, int mu) {
+  NEED_READY();
+  if (p < 0 || p >= h->cfg.P || mu < 0 || mu >= h->cfg.n_xi) return fail(h, DQA_EINVAL, "p or mu out of range");
+  return launch_truncate(h, p, mu);
+}
+extern "C" int dqa_apply_pattern(dqa_t* h, int p, int mu) {
+  int rc = dqa_canonize(h, p, mu);
+  if (rc) return rc;
+  return launch_truncate(h, p, mu);
+}
+
+extern "C" int dqa_apply_ux(dqa_t* h, double beta) {
+  NEED_READY();
+  const DqaDev& d = h->dev;
+  prof_a(h, 3);
+  DQA_LAUNCH(k_mixer, dim3(d.N, d.batch), dim3(128), 0, h->stream, d, std::cos(beta), std::sin(beta));
+  prof_b(h);
+  CK(cudaGetLastError());
+  return DQA_OK;
+}
+
+static int check_status(dqa_t* h) {
+  std::vector<int> st(h->cfg.batch);
+  CK(cudaMemcpyAsync(st.data(), h->dev.status, sizeof(int) * st.size(), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  for (size_t i = 0; i < st.size(); ++i)
+    if (st[i]) return fail(h, DQA_ENUMERIC, "instance %zu has status 0x%x (1 non-finite, 2 zero norm, 4 Jacobi not converged)", i, st[i]);
+  return DQA_OK;
+}
+
+extern "C" int dqa_step(dqa_t* h, int nsteps) {
+  NEED_READY();
+  if (nsteps < 0 || h->pp + nsteps > h->cfg.P) return fail(h, DQA_EINVAL, "step %d + %d exceeds P=%d", h->pp, nsteps, h->cfg.P);
+  for (int it = 0; it < nsteps; ++it) {
+    const int p = h->pp;
+    const double s_p = (double)(p + 1) / h->cfg.P;
+    const double beta = (1.0 - s_p) * h->cfg.dt;  // dQA_mps.py:88-89
+    for (int mu = 0; mu < h->cfg.n_xi; ++mu) {
+      int rc = launch_canonize(h, mu);
+      if (rc) return rc;
+      rc = launch_truncate(h, p, mu);
+      if (rc) return rc;
+    }
+    int rc = dqa_apply_ux(h, beta);
+    if (rc) return rc;
+    rc = launch_energy(h, p + 1);
+    if (rc) return rc;
+    h->pp++;
+  }
+  return check_status(h);
+}
+
+extern "C" int dqa_energy(dqa_t* h, double* eps) {
+  NEED_READY();
+  if (!eps) return DQA_EINVAL;
+  // slot P of the trace doubles as scratch only when the run is not finished; use a
+  // dedicated reduce into tmk-adjacent storage instead: reuse eps slot pp (it is rewritten by
+  // the step that owns it), then restore.
+  const DqaDev& d = h->dev;
+  std::vector<std::complex<double>> keep(d.batch), got(d.batch);
+  const int slot = h->pp;
+  for (int b = 0; b < d.batch; ++b)
+    CK(cudaMemcpyAsync(&keep[b], d.eps + (size_t)b * (d.P + 1) + slot, sizeof(cplx), cudaMemcpyDeviceToHost, h->stream));
+  int rc = launch_energy(h, slot);
+  if (rc) return rc;
+  for (int b = 0; b < d.batch; ++b)
+    CK(cudaMemcpyAsync(&got[b], d.eps + (size_t)b * (d.P + 1) + slot, sizeof(cplx), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  for (int b = 0; b < d.batch; ++b)
+    CK(cudaMemcpyAsync(d.eps + (size_t)b * (d.P + 1) + slot, &keep[b], sizeof(cplx), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  memcpy(eps, got.data(), sizeof(cplx) * d.batch);
+  return DQA_OK;
+}
+
+// ---- state access ----------------------------------------------------------------------
+extern "C" int dqa_get_bonds(dqa_t* h, int inst, int32_t* bonds) {
+  NEED_WS();
+  if (!bonds || inst < 0 || inst >= h->cfg.batch) return DQA_EINVAL;
+  CK(cudaMemcpyAsync(bonds, h->dev.bond + (size_t)inst * (h->cfg.N + 1), sizeof(int) * (h->cfg.N + 1), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return DQA_OK;
+}
+
+extern "C" int dqa_get_mps(dqa_t* h, int inst, int site, double* buf, int* l, int* r) {
+  NEED_WS();
+  const int N = h->cfg.N, chi = h->cfg.chi;
+  if (!buf || !l || !r || inst < 0 || inst >= h->cfg.batch || site < 0 || site >= N) return DQA_EINVAL;
+  int b[2];
+  CK(cudaMemcpyAsync(b, h->dev.bond + (size_t)inst * (N + 1) + site, sizeof(int) * 2, cudaMemcpyDeviceToHost, h->stream));
+  std::vector<std::complex<double>> pad((size_t)2 * chi * chi);
+  CK(cudaMemcpyAsync(pad.data(), h->dev.mps + ((size_t)inst * N + site) * 2 * chi * chi, sizeof(cplx) * pad.size(), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  *l = b[0];
+  *r = b[1];
+  std::complex<double>* out = reinterpret_cast<std::complex<double>*>(buf);
+  for (int a = 0; a < b[0]; ++a)
+    for (int s = 0; s < 2; ++s)
+      for (int c = 0; c < b[1]; ++c) out[((size_t)a * 2 + s) * b[1] + c] = pad[((size_t)a * 2 + s) * chi + c];
+  return DQA_OK;
+}
+
+extern "C" int dqa_set_mps(dqa_t* h, int inst, int site, const double* buf, int l, int r) {
+  NEED_WS();
+  const int N = h->cfg.N, chi = h->cfg.chi;
+  if (!buf || inst < 0 || inst >= h->cfg.batch || site < 0 || site >= N) return DQA_EINVAL;
+  if (l < 1 || r < 1 || l > chi || r > chi) return fail(h, DQA_ELIMIT, "site %d bonds (%d,%d) exceed chi=%d", site, l, r, chi);
+  if ((site == 0 && l != 1) || (site == N - 1 && r != 1)) return fail(h, DQA_EINVAL, "boundary bonds must be 1");
+  std::vector<std::complex<double>> pad((size_t)2 * chi * chi, std::complex<double>(0.0, 0.0));
+  const std::complex<double>* in = reinterpret_cast<const std::complex<double>*>(buf);
+  for (int a = 0; a < l; ++a)
+    for (int s = 0; s < 2; ++s)
+      for (int c = 0; c < r; ++c) pad[((size_t)a * 2 + s) * chi + c] = in[((size_t)a * 2 + s) * r + c];
+  int b[2] = {l, r};
+  CK(cudaMemcpyAsync(h->dev.mps + ((size_t)inst * N + site) * 2 * chi * chi, pad.data(), sizeof(cplx) * pad.size(), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->dev.bond + (size_t)inst * (N + 1) + site, b, sizeof(int) * 2, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  h->have_state = true;
+  return DQA_OK;
+}
+
+extern "C" int dqa_get_schmidt(dqa_t* h, int inst, int bond, double* s, int* n) {
+  NEED_WS();
+  const int N = h->cfg.N, chi = h->cfg.chi;
+  if (!s || !n || inst < 0 || inst >= h->cfg.batch || bond < 0 || bond >= N - 1) return DQA_EINVAL;
+  CK(cudaMemcpyAsync(n, h->dev.nsv + (size_t)inst * N + bond, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(s, h->dev.schmidt + ((size_t)inst * N + bond) * 2 * chi, sizeof(double) * 2 * chi, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return DQA_OK;
+}
+
+extern "C" int dqa_get_eps(dqa_t* h, double* eps) {
+  NEED_WS();
+  if (!eps) return DQA_EINVAL;
+  CK(cudaMemcpyAsync(eps, h->dev.eps, sizeof(cplx) * (size_t)h->cfg.batch * (h->cfg.P + 1), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return DQA_OK;
+}
+extern "C" int dqa_get_bd_monitor(dqa_t* h, int32_t* bd) {
+  NEED_WS();
+  if (!bd) return DQA_EINVAL;
+  CK(cudaMemcpyAsync(bd, h->dev.bdmon, sizeof(int) * (size_t)h->cfg.batch * h->cfg.P * h->cfg.n_xi, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return DQA_OK;
+}
+extern "C" int dqa_get_status(dqa_t* h, int32_t* st) {
+  NEED_WS();
+  if (!st) return DQA_EINVAL;
+  CK(cudaMemcpyAsync(st, h->dev.status, sizeof(int) * (size_t)h->cfg.batch, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return DQA_OK;
+}
+extern "C" int dqa_get_counters(dqa_t* h, uint64_t* c, int reset) {
+  NEED_WS();
+  if (!c) return DQA_EINVAL;
+  CK(cudaMemcpyAsync(c, h->dev.counters, sizeof(uint64_t) * 4 * (size_t)h->cfg.batch, cudaMemcpyDeviceToHost, h->stream));
+  if (reset) CK(cudaMemsetAsync(h->dev.counters, 0, sizeof(uint64_t) * 4 * (size_t)h->cfg.batch, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return DQA_OK;
+}
+
+// ---- ensemble moments (input of the one NCCL all-reduce) -------------------------------
+__global__ void k_ensemble_moments(DqaDev d, double* out) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s > d.P) return;
+  double m1 = 0.0, m2 = 0.0, ok = 0.0;
+  for (int b = 0; b < d.batch; ++b) {
+    if (d.status[b]) continue;
+    const double v = d.eps[(size_t)b * (d.P + 1) + s].x;
+    m1 += v;
+    m2 += v * v;
+    ok += 1.0;
+  }
+  out[s] = m1;
+  out[(d.P + 1) + s] = m2;
+  out[2 * (d.P + 1) + s] = ok;
+}
+
+extern "C" int dqa_ensemble_moments(dqa_t* h, double* device_out) {
+  NEED_WS();
+  if (!device_out) return DQA_EINVAL;
+  const int n = h->cfg.P + 1;
+  DQA_LAUNCH(k_ensemble_moments, dim3((n + 127) / 128), dim3(128), 0, h->stream, h->dev, device_out);
+  CK(cudaGetLastError());
+  return DQA_OK;
+}
+
+// ---- FP64 peak microbenchmark ----------------------------------------------------------
+__global__ void k_fp64_peak(double* out, int iters) {
+  double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+  const double m = 1.0000001, c = 1e-9;
+  for (int i = 0; i < iters; ++i) {
+    a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+    a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+extern "C" int dqa_measure_fp64_peak(dqa_t* h, double* tflops) {
+  NEED_WS();
+  if (!tflops) return DQA_EINVAL;
+  // scratch: the LQ work buffer (>= 2*chi*ld_theta*batch complex)
+  const size_t cap = (size_t)h->cfg.batch * 2 * h->cfg.chi * h->dev.ld_theta * 2;  // doubles
+  int blocks = 148 * 8, threads = 256;
+  while ((size_t)blocks * threads > cap && blocks > 1) blocks /= 2;
+  if ((size_t)blocks * threads > cap) return fail(h, DQA_ELIMIT, "workspace too small for the FP64 probe");
+#ifdef DQA_EMUL
+  *tflops = 0.0;
+  return DQA_OK;
+#endif
+  const int iters = 1 << 16;
+  cudaEvent_t a, b;
+  CK(cudaEventCreate(&a));
+  CK(cudaEventCreate(&b));
+  double best = 0.0;
+  for (int rep = 0; rep < 4; ++rep) {
+    CK(cudaEventRecord(a, h->stream));
+    DQA_LAUNCH(k_fp64_peak, dim3(blocks), dim3(threads), 0, h->stream, (double*)h->dev.work, iters);
+    CK(cudaEventRecord(b, h->stream));
+    CK(cudaEventSynchronize(b));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, a, b));
+    const double fl = 2.0 * 8.0 * iters * (double)blocks * threads;
+    if (ms > 0.f && fl / (ms * 1e-3) / 1e12 > best) best = fl / (ms * 1e-3) / 1e12;
+  }
+  cudaEventDestroy(a);
+  cudaEventDestroy(b);
+  *tflops = best;
+  return DQA_OK;
+}

@@ -1,0 +1,123 @@
+// dqa_common.cuh -- shared definitions for the sm_100a dQA kernels.
+//
+// Built two ways: nvcc (the product, libdqa.so) and, with -DDQA_EMUL, g++ on top of
+// tests/emul/cuda_emul.h (a fiber SIMT emulator used only by the CPU test-suite to
+// debug kernel logic; never loaded by the package).
+#pragma once
+
+#ifdef DQA_EMUL
+#include "cuda_emul.h"
+#define DQA_LAUNCH(kernel, grid, block, smem, stream, ...) \
+  ::emul::launch((grid), (block), (smem), [=]() { kernel(__VA_ARGS__); })
+#define DQA_DYN_SMEM(name) char* name = ::emul::dyn_smem_
+#else
+#include <cuda_runtime.h>
+#define DQA_LAUNCH(kernel, grid, block, smem, stream, ...) \
+  kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#define DQA_DYN_SMEM(name) extern __shared__ __align__(16) char name[]
+#endif
+
+#include <stdint.h>
+
+typedef double2 cplx;
+
+#define DQA_FULL 0xffffffffu
+
+// ---------------------------------------------------------------------------------
+// complex128 helpers (interleaved re,im == the reference's numpy complex128 layout)
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ cplx cmk(double x, double y) { return make_double2(x, y); }
+__device__ __forceinline__ cplx cadd(cplx a, cplx b) { return cmk(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ cplx csub(cplx a, cplx b) { return cmk(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ cplx cmul(cplx a, cplx b) { return cmk(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+// a * conj(b)
+__device__ __forceinline__ cplx cmulc(cplx a, cplx b) { return cmk(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y); }
+__device__ __forceinline__ cplx cscale(cplx a, double s) { return cmk(a.x * s, a.y * s); }
+__device__ __forceinline__ cplx cconj(cplx a) { return cmk(a.x, -a.y); }
+// acc + a*b
+__device__ __forceinline__ cplx cfma(cplx a, cplx b, cplx acc) {
+  acc.x = fma(a.x, b.x, acc.x);
+  acc.x = fma(-a.y, b.y, acc.x);
+  acc.y = fma(a.x, b.y, acc.y);
+  acc.y = fma(a.y, b.x, acc.y);
+  return acc;
+}
+// acc + a*conj(b)
+__device__ __forceinline__ cplx cfmac(cplx a, cplx b, cplx acc) {
+  acc.x = fma(a.x, b.x, acc.x);
+  acc.x = fma(a.y, b.y, acc.x);
+  acc.y = fma(a.y, b.x, acc.y);
+  acc.y = fma(-a.x, b.y, acc.y);
+  return acc;
+}
+// acc - a*b
+__device__ __forceinline__ cplx cfms(cplx a, cplx b, cplx acc) {
+  acc.x = fma(-a.x, b.x, acc.x);
+  acc.x = fma(a.y, b.y, acc.x);
+  acc.y = fma(-a.x, b.y, acc.y);
+  acc.y = fma(-a.y, b.x, acc.y);
+  return acc;
+}
+__device__ __forceinline__ double cabs2(cplx a) { return fma(a.x, a.x, a.y * a.y); }
+__device__ __forceinline__ cplx crecip(cplx a) {
+  double d = 1.0 / cabs2(a);
+  return cmk(a.x * d, -a.y * d);
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(DQA_FULL, v, o);
+  return v;
+}
+__device__ __forceinline__ cplx warp_sum(cplx v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    v.x += __shfl_xor_sync(DQA_FULL, v.x, o);
+    v.y += __shfl_xor_sync(DQA_FULL, v.y, o);
+  }
+  return v;
+}
+
+// ---------------------------------------------------------------------------------
+// device-side view of one plan (all pointers are caller-owned device memory, carved
+// out of the workspace bound with dqa_bind_workspace)
+// ---------------------------------------------------------------------------------
+struct DqaDev {
+  int N, D, n_xi, chi, batch, P;
+  int smax;        // N+1 sectors at most per bond
+  int ld_theta;    // row stride of Theta (>= chi*(N+1))
+  int nsec_total;  // number of (site, sector) Q blocks per instance
+  int kh;          // D/2+1: independent Fourier modes of the energy sweep
+  int max_sweeps;
+  double cutoff;
+  cplx* mps;              // [batch][N][chi*2*chi]   site (a,s,c) at (a*2+s)*chi + c
+  int* bond;              // [batch][N+1]
+  const uint8_t* hbit;    // [batch][n_xi][N]        (1 - xi)/2
+  const cplx* uz;         // [P][D]                  u_p(x) = exp(-i gamma_p f(x))
+  const cplx* gk;         // [D]                     fxft[k]/sqrt(D)
+  const cplx* phase;      // [D]                     exp(2 pi i k / D) = exp(i pi q / D), q = 2k
+  cplx* rbuf;             // [batch][2][smax][chi*chi]     R_{n,y} row-major (q x b_n), ld chi
+  cplx* qbuf;             // [batch][nsec_total][2chi*chi] Q_{n,y} col-major (m x q),  ld 2chi
+  int* qdim;              // [batch][N+1][smax]            q_{n,y}
+  cplx* theta;            // [batch][2][2chi*ld_theta]     Theta_l row-major, ping-pong on l
+  cplx* work;             // [batch][2chi*ld_theta]        LQ scratch
+  double* scale;          // [batch]                       renorm factor of the last truncation
+  double* schmidt;        // [batch][N][2chi]              singular values seen at cut l
+  int* nsv;               // [batch][N]
+  cplx* tmk;              // [batch][n_xi][kh]             <psi|Phi_{mu,k}|psi>
+  cplx* eps;              // [batch][P+1]
+  int* bdmon;             // [batch][P*n_xi]
+  int* status;            // [batch]  bit0: non-finite, bit1: zero norm, bit2: Jacobi not converged
+  unsigned long long* counters;  // [batch][4] rotations, sweeps, svds, qr columns
+};
+
+__host__ __device__ __forceinline__ int dqa_secbase(int N, int n) {
+  // offset of site n's first Q block; site n (1..N-1) has sectors y = 0..N-n
+  return (n - 1) * (N + 1) - (n - 1) * n / 2;
+}
+
+enum {
+  DQA_ST_NONFINITE = 1,
+  DQA_ST_ZERONORM = 2,
+  DQA_ST_NOCONV = 4,
+};

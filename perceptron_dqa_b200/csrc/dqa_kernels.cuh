@@ -1,0 +1,613 @@
+// dqa_kernels.cuh -- hand-written sm_100a kernels of the dQA MPS step (fused "sector" path).
+//
+// One dQA sub-step for pattern mu (reference: dQA_mps.py:92-106) is
+//     psi <- truncate_chi( right_canonise( U_z^mu psi ) )
+// with U_z^mu = exp(-i gamma_p f(X_mu)) (lib/dQA_utils.py:32-75 builds it as a bond-(N+1)
+// Fourier MPO; X_mu = Hamming distance to pattern mu).  Instead of the reference's
+// bond-(chi*(N+1)) direct-sum tensors we label the bond between sites n-1 and n by
+// (c, y): c = MPS bond index, y = number of mismatches on sites >= n.  Different y are
+// orthogonal, so:
+//   k_sector_qr   right-canonisation (lib/tenn.py:152-190) = independent Householder QRs,
+//                 one CTA per (site, sector y, instance), operand (q_y + q_{y-1}) x b in SMEM;
+//   k_theta0/k_theta  build the centre matrix Theta_l (2c_l x sum_y q_y) of the left-to-right
+//                 sweep from the sector Q blocks (lib/tenn.py:248 tensordot, block-sparse);
+//   k_svd         per instance: Householder LQ of Theta_l, one-sided Jacobi SVD of the
+//                 (2c x 2c) factor with warp-shuffle reductions, the reference's trim rule
+//                 (cutoff 1e-10 on relative cumulative s^2, clamp to chi, renormalise;
+//                 lib/tenn.py:317-354) and the new left-orthonormal site tensor.
+//   k_mixer       exp(+i beta sigma^x) on every physical leg (lib/dQA_utils.py:26-30).
+//   k_energy      transfer-matrix sweep for <psi|Phi_{mu,k}|psi> (dQA_mps.py:68-81,
+//                 lib/tenn.py:93-109), one CTA per (k, mu, instance), using
+//                 T_{mu,D-k} = conj(T_{mu,k}).
+// All arithmetic is complex128; only gauge-invariant results are promised to match the
+// reference.
+#pragma once
+#include "dqa_common.cuh"
+
+// ---------------------------------------------------------------------------------
+// block-wide sum, result broadcast to every thread (red: >= 33 doubles of shared memory)
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ double block_sum(double v, double* red) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
+  v = warp_sum(v);
+  __syncthreads();  // protect red[] against the previous use
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  double t = 0.0;
+  for (int w = 0; w < nwarp; ++w) t += red[w];
+  return t;
+}
+
+// Householder generator (LAPACK zlarfg semantics without the safmin loop): given alpha and
+// ss = |x[1:]|^2 returns beta (real), tau, and scal = 1/(alpha-beta); H^H [alpha;x] = [beta;0],
+// H = I - tau v v^H, v = [1; x*scal].
+__device__ __forceinline__ void householder_gen(cplx alpha, double ss, double& beta, cplx& tau, cplx& scal) {
+  if (ss == 0.0 && alpha.y == 0.0) {
+    beta = alpha.x;
+    tau = cmk(0.0, 0.0);
+    scal = cmk(0.0, 0.0);
+  } else {
+    double nrm = sqrt(cabs2(alpha) + ss);
+    beta = (alpha.x >= 0.0) ? -nrm : nrm;
+    tau = cmk((beta - alpha.x) / beta, -alpha.y / beta);
+    scal = crecip(cmk(alpha.x - beta, alpha.y));
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// integer pattern tables (implicit in lib/dQA_utils.py:50-53,106)
+//   hbit = (1-xi)/2, e = 1 - xi*(-1)^s = 2*(hbit^s), q = k*e.  Pure integer arithmetic.
+// ---------------------------------------------------------------------------------
+__global__ void k_hamming_tables(const int8_t* xi, int n_items, int D, uint8_t* hbit, int32_t* e, int32_t* q) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_items; i += gridDim.x * blockDim.x) {
+    const int x = xi[i];
+    const int hb = (1 - x) / 2;
+    if (hbit) hbit[i] = (uint8_t)hb;
+    for (int s = 0; s < 2; ++s) {
+      const int es = 1 - x * (s ? -1 : 1);
+      if (e) e[i * 2 + s] = es;
+      if (q)
+        for (int k = 0; k < D; ++k) q[(i * 2 + s) * D + k] = k * es;
+    }
+  }
+}
+
+// |+>^N, bond 1 everywhere (dQA_mps.py:139); also resets the per-instance status words.
+__global__ void k_init_plus(DqaDev d) {
+  const int inst = blockIdx.x;
+  const int site_sz = d.chi * 2 * d.chi;
+  cplx* m = d.mps + (size_t)inst * d.N * site_sz;
+  for (int i = threadIdx.x; i < d.N * site_sz; i += blockDim.x) {
+    const int r = i % site_sz;
+    m[i] = (r == 0 || r == d.chi) ? cmk(0.70710678118654757, 0.0) : cmk(0.0, 0.0);
+  }
+  for (int i = threadIdx.x; i <= d.N; i += blockDim.x) d.bond[inst * (d.N + 1) + i] = 1;
+  if (threadIdx.x == 0) {
+    d.status[inst] = 0;
+    d.scale[inst] = 1.0;
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// k_sector_qr: one (site n, sector y, instance) block of the right-canonisation sweep.
+//   M[(s,j), a] = sum_c R_{n+1, y-nbit(s)}[j,c] * A_n[a,s,c]      (m x b_n, m = q0+q1)
+//   M = Q R (Householder, R diagonal made real >= 0 as qr_stabilized does, with sgn(0):=+1)
+// shared memory: M (2chi x chi, col-major) | As (2*chi*chi) | Rs (2chi x (chi+1)) | tau | beta
+// ---------------------------------------------------------------------------------
+__host__ __device__ inline size_t sector_qr_smem(int chi) {
+  return sizeof(cplx) * ((size_t)2 * chi * chi + 2 * chi * chi + 2 * chi * (chi + 1) + chi) + sizeof(double) * chi;
+}
+
+__global__ void k_sector_qr(DqaDev d, int n, int mu) {
+  DQA_DYN_SMEM(smraw);
+  const int y = blockIdx.x, inst = blockIdx.y;
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarp = nt >> 5;
+  const int chi = d.chi, ldm = 2 * chi, ldr = chi + 1;
+  cplx* M = (cplx*)smraw;
+  cplx* As = M + (size_t)ldm * chi;
+  cplx* Rs = As + (size_t)2 * chi * chi;
+  cplx* tau = Rs + (size_t)2 * chi * ldr;
+  double* betas = (double*)(tau + chi);
+
+  const int* bond = d.bond + inst * (d.N + 1);
+  const int bl = bond[n], br = bond[n + 1];
+  const int hb = d.hbit[((size_t)inst * d.n_xi + mu) * d.N + n];
+  const int ymax_in = d.N - n - 1;  // sectors of bond n+1 are 0..N-n-1
+  const int* qd_in = d.qdim + ((size_t)inst * (d.N + 1) + (n + 1)) * d.smax;
+  const int yp0 = y - hb, yp1 = y - (hb ^ 1);
+  const int q0 = (yp0 >= 0 && yp0 <= ymax_in) ? qd_in[yp0] : 0;
+  const int q1 = (yp1 >= 0 && yp1 <= ymax_in) ? qd_in[yp1] : 0;
+  const int m = q0 + q1;
+  const int q = m < bl ? m : bl;
+  const size_t rsz = (size_t)chi * chi;
+  const cplx* rin = d.rbuf + ((size_t)inst * 2 + ((n + 1) & 1)) * d.smax * rsz;
+  cplx* rout = d.rbuf + (((size_t)inst * 2 + (n & 1)) * d.smax + y) * rsz;
+  const cplx* a_site = d.mps + ((size_t)inst * d.N + n) * (2 * rsz);
+
+  // stage A_n (both s) and the two R blocks
+  for (int i = tid; i < bl * 2 * br; i += nt) {
+    const int c = i % br, as = i / br;
+    As[as * br + c] = a_site[as * chi + c];
+  }
+  for (int i = tid; i < m * br; i += nt) {
+    const int c = i % br, row = i / br;
+    const int s = row < q0 ? 0 : 1;
+    const int j = row - (s ? q0 : 0);
+    const int yp = s ? yp1 : yp0;
+    Rs[row * ldr + c] = rin[(size_t)yp * rsz + j * chi + c];
+  }
+  __syncthreads();
+  for (int i = tid; i < m * bl; i += nt) {
+    const int row = i % m, a = i / m;
+    const int s = row < q0 ? 0 : 1;
+    const cplx* rr = Rs + row * ldr;
+    const cplx* aa = As + (a * 2 + s) * br;
+    cplx acc = cmk(0.0, 0.0);
+    for (int c = 0; c < br; ++c) acc = cfma(rr[c], aa[c], acc);
+    M[row + a * ldm] = acc;
+  }
+  __syncthreads();
+
+  // Householder QR, column by column (zgeqr2)
+  for (int k = 0; k < q; ++k) {
+    if (warp == 0) {
+      double ss = 0.0;
+      for (int i = k + 1 + lane; i < m; i += 32) ss += cabs2(M[i + k * ldm]);
+      ss = warp_sum(ss);
+      const cplx alpha = M[k + k * ldm];
+      double beta;
+      cplx t, scal;
+      householder_gen(alpha, ss, beta, t, scal);
+      __syncwarp();
+      for (int i = k + 1 + lane; i < m; i += 32) M[i + k * ldm] = cmul(M[i + k * ldm], scal);
+      if (lane == 0) {
+        tau[k] = t;
+        betas[k] = beta;
+        M[k + k * ldm] = cmk(beta, 0.0);
+      }
+    }
+    __syncthreads();
+    const cplx tk = cconj(tau[k]);  // H^H is applied
+    if (tk.x != 0.0 || tk.y != 0.0) {
+      for (int j = k + 1 + warp; j < bl; j += nwarp) {
+        cplx w = (lane == 0) ? M[k + j * ldm] : cmk(0.0, 0.0);
+        for (int i = k + 1 + lane; i < m; i += 32) w = cfmac(M[i + j * ldm], M[i + k * ldm], w);  // M_ij * conj(v_i)
+        w = warp_sum(w);
+        const cplx tw = cmul(tk, w);
+        if (lane == 0) M[k + j * ldm] = csub(M[k + j * ldm], tw);
+        for (int i = k + 1 + lane; i < m; i += 32) M[i + j * ldm] = cfms(tw, M[i + k * ldm], M[i + j * ldm]);
+      }
+    }
+    __syncthreads();
+  }
+
+  // R out (row-major q x bl, ld chi), diagonal made non-negative
+  for (int i = tid; i < q * bl; i += nt) {
+    const int a = i % bl, j = i / bl;
+    cplx v = cmk(0.0, 0.0);
+    if (a >= j) {
+      v = M[j + a * ldm];
+      if (betas[j] < 0.0) v = cmk(-v.x, -v.y);
+    }
+    rout[j * chi + a] = v;
+  }
+  __syncthreads();
+
+  // form Q in place (zung2r)
+  for (int i = q - 1; i >= 0; --i) {
+    const cplx ti = tau[i];
+    if (ti.x != 0.0 || ti.y != 0.0) {
+      for (int j = i + 1 + warp; j < q; j += nwarp) {
+        cplx w = cmk(0.0, 0.0);
+        for (int r = i + 1 + lane; r < m; r += 32) w = cfmac(M[r + j * ldm], M[r + i * ldm], w);
+        w = warp_sum(w);
+        const cplx tw = cmul(ti, w);
+        if (lane == 0) M[i + j * ldm] = cmk(-tw.x, -tw.y);
+        for (int r = i + 1 + lane; r < m; r += 32) M[r + j * ldm] = cfms(tw, M[r + i * ldm], M[r + j * ldm]);
+      }
+    }
+    __syncthreads();
+    const cplx nti = cmk(-ti.x, -ti.y);
+    for (int r = i + 1 + tid; r < m; r += nt) M[r + i * ldm] = cmul(nti, M[r + i * ldm]);
+    for (int r = tid; r < i; r += nt) M[r + i * ldm] = cmk(0.0, 0.0);
+    if (tid == 0) M[i + i * ldm] = cmk(1.0 - ti.x, -ti.y);
+    __syncthreads();
+  }
+
+  cplx* qout = d.qbuf + ((size_t)inst * d.nsec_total + dqa_secbase(d.N, n) + y) * (2 * rsz);
+  for (int i = tid; i < m * q; i += nt) {
+    const int row = i % m, j = i / m;
+    cplx v = M[row + j * ldm];
+    if (betas[j] < 0.0) v = cmk(-v.x, -v.y);
+    qout[row + j * ldm] = v;
+  }
+  if (tid == 0) {
+    d.qdim[((size_t)inst * (d.N + 1) + n) * d.smax + y] = q;
+    atomicAdd(&d.counters[inst * 4 + 3], (unsigned long long)q);
+  }
+}
+
+// bond N has one sector (y=0) of dimension 1 with R = [1]
+__global__ void k_sector_init(DqaDev d) {
+  const int inst = blockIdx.x;
+  if (threadIdx.x == 0) {
+    d.qdim[((size_t)inst * (d.N + 1) + d.N) * d.smax + 0] = 1;
+    d.rbuf[(((size_t)inst * 2 + (d.N & 1)) * d.smax + 0) * d.chi * d.chi] = cmk(1.0, 0.0);
+  }
+}
+
+__device__ __forceinline__ int qdim_prefix(const int* qd, int y) {
+  int o = 0;
+  for (int i = 0; i < y; ++i) o += qd[i];
+  return o;
+}
+
+// ---------------------------------------------------------------------------------
+// k_theta0: Theta_0[(s), (j,y')] = u_p(y' + nbit_0(s)) * sum_c R_{1,y'}[j,c] A_0[0,s,c]
+// grid (N sectors of bond 1, batch)
+// ---------------------------------------------------------------------------------
+__global__ void k_theta0(DqaDev d, int mu, int p) {
+  const int yp = blockIdx.x, inst = blockIdx.y, tid = threadIdx.x, nt = blockDim.x;
+  const int chi = d.chi;
+  const int* qd = d.qdim + ((size_t)inst * (d.N + 1) + 1) * d.smax;
+  const int qn = qd[yp], off = qdim_prefix(qd, yp);
+  const int br = d.bond[inst * (d.N + 1) + 1];
+  const int hb = d.hbit[((size_t)inst * d.n_xi + mu) * d.N + 0];
+  const size_t rsz = (size_t)chi * chi;
+  const cplx* r1 = d.rbuf + (((size_t)inst * 2 + 1) * d.smax + yp) * rsz;
+  const cplx* a0 = d.mps + ((size_t)inst * d.N) * (2 * rsz);
+  cplx* th = d.theta + ((size_t)inst * 2 + 0) * (size_t)(2 * chi) * d.ld_theta;
+  for (int i = tid; i < 2 * qn; i += nt) {
+    const int j = i % qn, s = i / qn;
+    cplx acc = cmk(0.0, 0.0);
+    for (int c = 0; c < br; ++c) acc = cfma(r1[j * chi + c], a0[s * chi + c], acc);
+    const cplx u = d.uz[(size_t)p * d.D + yp + (hb ^ s)];
+    th[(size_t)s * d.ld_theta + off + j] = cmul(u, acc);
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// k_theta (l >= 1): absorb the previous cut's S V^H and contract with the sector Q blocks.
+//   C_y[beta,j]   = scale * sum_r conj(U[r,beta]) Theta_{l-1}[r, off_y + j]      (U = new site l-1)
+//   Theta_l[(beta,s), off'_{y'} + j'] = sum_j C_y[beta,j] Q_{l,y}[(rowoff_s + j'), j],  y' = y - nbit_l(s)
+// grid (N-l+1 sectors of bond l, batch); shared: C (chi x chi)
+// ---------------------------------------------------------------------------------
+__global__ void k_theta(DqaDev d, int l, int mu) {
+  DQA_DYN_SMEM(smraw);
+  cplx* C = (cplx*)smraw;
+  const int y = blockIdx.x, inst = blockIdx.y, tid = threadIdx.x, nt = blockDim.x;
+  const int chi = d.chi, ldq = 2 * chi, ld = d.ld_theta;
+  const size_t rsz = (size_t)chi * chi;
+  const int* bond = d.bond + inst * (d.N + 1);
+  const int cl = bond[l], mrp = 2 * bond[l - 1];
+  const int* qd = d.qdim + ((size_t)inst * (d.N + 1) + l) * d.smax;
+  const int* qd1 = qd + d.smax;
+  const int qy = qd[y], offy = qdim_prefix(qd, y);
+  const int hb = d.hbit[((size_t)inst * d.n_xi + mu) * d.N + l];
+  const int ymax_out = d.N - l - 1;
+  const cplx* thp = d.theta + ((size_t)inst * 2 + ((l - 1) & 1)) * (size_t)(2 * chi) * ld;
+  cplx* thc = d.theta + ((size_t)inst * 2 + (l & 1)) * (size_t)(2 * chi) * ld;
+  const cplx* U = d.mps + ((size_t)inst * d.N + (l - 1)) * (2 * rsz);
+  const double scale = d.scale[inst];
+  for (int i = tid; i < cl * qy; i += nt) {
+    const int j = i % qy, b = i / qy;
+    cplx acc = cmk(0.0, 0.0);
+    for (int r = 0; r < mrp; ++r) acc = cfmac(thp[(size_t)r * ld + offy + j], U[r * chi + b], acc);
+    C[b * qy + j] = cscale(acc, scale);
+  }
+  __syncthreads();
+  const cplx* Q = d.qbuf + ((size_t)inst * d.nsec_total + dqa_secbase(d.N, l) + y) * (2 * rsz);
+  const int yp0 = y - hb, yp1 = y - (hb ^ 1);
+  const int v0 = (yp0 >= 0 && yp0 <= ymax_out), v1 = (yp1 >= 0 && yp1 <= ymax_out);
+  const int q0 = v0 ? qd1[yp0] : 0;
+  for (int s = 0; s < 2; ++s) {
+    const int yp = s ? yp1 : yp0;
+    if (!(s ? v1 : v0)) continue;
+    const int qo = qd1[yp], offo = qdim_prefix(qd1, yp), rowoff = s ? q0 : 0;
+    for (int i = tid; i < cl * qo; i += nt) {
+      const int jp = i % qo, b = i / qo;
+      cplx acc = cmk(0.0, 0.0);
+      for (int j = 0; j < qy; ++j) acc = cfma(C[b * qy + j], Q[(rowoff + jp) + j * ldq], acc);
+      thc[(size_t)(b * 2 + s) * ld + offo + jp] = acc;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// k_svd: truncation at cut l for one instance (lib/tenn.py:229-252, :307-405).
+//   work <- Theta_l; Householder LQ (rows), L (mr x k) to shared; one-sided Jacobi on the
+//   columns of L (right rotations, one warp per column pair, round-robin ordering);
+//   sigma = column norms, sorted; trim rule; new site l = U_kept reshaped (c_l,2,n_chi).
+// shared: L (2chi x 2chi col-major) | sig, ssorted (2chi doubles each) | order (2chi ints) | red
+// ---------------------------------------------------------------------------------
+__host__ __device__ inline size_t svd_smem(int chi) {
+  return sizeof(cplx) * (size_t)(2 * chi) * (2 * chi) + sizeof(double) * (4 * chi + 64) + sizeof(int) * (2 * chi + 8);
+}
+
+__device__ __forceinline__ void rr_pair(int n, int round, int idx, int& p, int& q) {
+  // circle method on n (even) players: round in [0,n-2], idx in [0,n/2)
+  if (idx == 0) {
+    p = n - 1;
+    q = round;
+  } else {
+    p = (round + idx) % (n - 1);
+    q = (round - idx + (n - 1)) % (n - 1);
+  }
+  if (p > q) {
+    const int t = p;
+    p = q;
+    q = t;
+  }
+}
+
+__global__ void k_svd(DqaDev d, int l, int mu, int p_step) {
+  DQA_DYN_SMEM(smraw);
+  const int inst = blockIdx.x, tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarp = nt >> 5;
+  const int chi = d.chi, ld = d.ld_theta;
+  const size_t rsz = (size_t)chi * chi;
+  cplx* L = (cplx*)smraw;
+  double* sig = (double*)(L + (size_t)(2 * chi) * (2 * chi));
+  double* ssorted = sig + 2 * chi;
+  double* red = ssorted + 2 * chi;  // 64 doubles
+  int* order = (int*)(red + 64);
+  int* sh_i = order + 2 * chi;  // [0]=rotation count, [1]=n_chi
+  int* bond = d.bond + inst * (d.N + 1);
+  const int mr = 2 * bond[l];
+  const int* qd1 = d.qdim + ((size_t)inst * (d.N + 1) + (l + 1)) * d.smax;
+  const int Q = qdim_prefix(qd1, d.N - l);  // sectors 0..N-l-1
+  const int k = mr < Q ? mr : Q;
+  const int ldl = mr;
+  const cplx* th = d.theta + ((size_t)inst * 2 + (l & 1)) * (size_t)(2 * chi) * ld;
+  cplx* wk = d.work + (size_t)inst * (size_t)(2 * chi) * ld;
+
+  for (int i = tid; i < mr * Q; i += nt) {
+    const int c = i % Q, r = i / Q;
+    wk[(size_t)r * ld + c] = th[(size_t)r * ld + c];
+  }
+  __syncthreads();
+
+  // ---- Householder LQ on rows of wk ------------------------------------------------
+  for (int kk = 0; kk < k; ++kk) {
+    cplx* row = wk + (size_t)kk * ld;
+    double ss = 0.0;
+    for (int j = kk + 1 + tid; j < Q; j += nt) ss += cabs2(row[j]);
+    const cplx alpha = row[kk];
+    ss = block_sum(ss, red);
+    double beta;
+    cplx t, scal;
+    householder_gen(cconj(alpha), ss, beta, t, scal);
+    // v = conj(x[1:])*scal  ->  stored conj(v) = x[1:] * conj(scal)
+    const cplx cs = cconj(scal);
+    for (int j = kk + 1 + tid; j < Q; j += nt) row[j] = cmul(row[j], cs);
+    __syncthreads();
+    if (tid == 0) row[kk] = cmk(beta, 0.0);
+    if (t.x != 0.0 || t.y != 0.0) {
+      for (int r = kk + 1 + warp; r < mr; r += nwarp) {
+        cplx* yr = wk + (size_t)r * ld;
+        cplx w = (lane == 0) ? yr[kk] : cmk(0.0, 0.0);
+        for (int j = kk + 1 + lane; j < Q; j += 32) w = cfmac(yr[j], row[j], w);  // y_j * conj(vbar_j)
+        w = warp_sum(w);
+        const cplx tw = cmul(t, w);
+        if (lane == 0) yr[kk] = csub(yr[kk], tw);
+        for (int j = kk + 1 + lane; j < Q; j += 32) yr[j] = cfms(tw, row[j], yr[j]);
+      }
+    }
+    __syncthreads();
+  }
+  for (int i = tid; i < mr * k; i += nt) {
+    const int r = i % mr, c = i / mr;
+    L[r + c * ldl] = (c <= r) ? wk[(size_t)r * ld + c] : cmk(0.0, 0.0);
+  }
+  __syncthreads();
+
+  // ---- one-sided Jacobi on the columns of L ----------------------------------------
+  const int kp = k + (k & 1);
+  const double tol = sqrt((double)mr) * 2.220446049250313e-16;
+  int sweeps = 0, converged = (k <= 1);
+  unsigned long long nrot_total = 0;
+  for (int sweep = 0; sweep < d.max_sweeps && !converged; ++sweep) {
+    if (tid == 0) sh_i[0] = 0;
+    __syncthreads();
+    for (int round = 0; round < kp - 1; ++round) {
+      for (int pr = warp; pr < kp / 2; pr += nwarp) {
+        int p, q;
+        rr_pair(kp, round, pr, p, q);
+        if (q >= k) continue;  // padded dummy column (warp-uniform)
+        cplx* xp = L + p * ldl;
+        cplx* xq = L + q * ldl;
+        double a = 0.0, b = 0.0;
+        cplx g = cmk(0.0, 0.0);
+        for (int r = lane; r < mr; r += 32) {
+          const cplx vp = xp[r], vq = xq[r];
+          a += cabs2(vp);
+          b += cabs2(vq);
+          g = cfmac(vq, vp, g);  // conj(xp) * xq
+        }
+        a = warp_sum(a);
+        b = warp_sum(b);
+        g = warp_sum(g);
+        const double ag = sqrt(cabs2(g));
+        if (ag > tol * sqrt(a * b) && ag > 0.0) {
+          const double zeta = (b - a) / (2.0 * ag);
+          const double tt = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+          const double c = 1.0 / sqrt(1.0 + tt * tt);
+          const double s = c * tt;
+          const cplx ph = cmk(g.x / ag, -g.y / ag);  // e^{-i phi}
+          const cplx sph = cscale(ph, s), cph = cscale(ph, c);
+          for (int r = lane; r < mr; r += 32) {
+            const cplx vp = xp[r], vq = xq[r];
+            xp[r] = cfms(sph, vq, cscale(vp, c));  // c*xp - s e^{-i phi} xq
+            xq[r] = cfma(cph, vq, cscale(vp, s));  // s*xp + c e^{-i phi} xq
+          }
+          if (lane == 0) atomicAdd(&sh_i[0], 1);
+        }
+      }
+      __syncthreads();
+    }
+    sweeps++;
+    nrot_total += (unsigned long long)sh_i[0];
+    converged = (sh_i[0] == 0);
+    __syncthreads();
+  }
+
+  // ---- singular values, ordering, trim rule ------------------------------------------
+  for (int j = warp; j < k; j += nwarp) {
+    double a = 0.0;
+    for (int r = lane; r < mr; r += 32) a += cabs2(L[r + j * ldl]);
+    a = warp_sum(a);
+    if (lane == 0) sig[j] = sqrt(a);
+  }
+  for (int j = tid; j < k; j += nt) order[j] = j;
+  __syncthreads();
+  for (int j = tid; j < k; j += nt) {
+    const double sj = sig[j];
+    int rank = 0;
+    for (int i = 0; i < k; ++i) {
+      const double si = sig[i];
+      rank += (si > sj) || (si == sj && i < j);
+    }
+    if (sj == sj) {  // NaN keeps the identity slot
+      order[rank] = j;
+      ssorted[rank] = sj;
+    } else {
+      ssorted[j] = sj;
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    double tot = 0.0;
+    for (int i = 0; i < k; ++i) tot += ssorted[i] * ssorted[i];
+    const double thr = (1.0 - d.cutoff) * tot;
+    double csp = 0.0, ckeep = 0.0;
+    int cnt = 0;
+    for (int i = 0; i < k; ++i) {
+      csp += ssorted[i] * ssorted[i];
+      if (csp < thr) cnt++;
+    }
+    int n_chi = cnt + 1;
+    if (n_chi < 1) n_chi = 1;
+    if (n_chi > chi) n_chi = chi;
+    if (n_chi > k) n_chi = k;
+    for (int i = 0; i < n_chi; ++i) ckeep += ssorted[i] * ssorted[i];
+    double sc = 1.0;
+    int st = 0;
+    if (!(tot == tot) || tot > 1e300) st |= DQA_ST_NONFINITE;
+    if (tot == 0.0) st |= DQA_ST_ZERONORM;
+    if (!converged) st |= DQA_ST_NOCONV;
+    if (n_chi < k && ckeep > 0.0) sc = sqrt(tot / ckeep);
+    if (st) atomicOr(&d.status[inst], st);
+    sh_i[1] = n_chi;
+    d.scale[inst] = sc;
+    bond[l + 1] = n_chi;
+    d.nsv[inst * d.N + l] = k;
+    atomicAdd(&d.counters[inst * 4 + 0], nrot_total);
+    atomicAdd(&d.counters[inst * 4 + 1], (unsigned long long)sweeps);
+    atomicAdd(&d.counters[inst * 4 + 2], 1ull);
+    if (l == d.N - 1) d.bdmon[(size_t)inst * d.P * d.n_xi + (size_t)p_step * d.n_xi + mu] = bond[d.N / 2];
+  }
+  __syncthreads();
+  const int n_chi = sh_i[1];
+  for (int i = tid; i < k; i += nt) d.schmidt[((size_t)inst * d.N + l) * (2 * chi) + i] = ssorted[i];
+  cplx* site = d.mps + ((size_t)inst * d.N + l) * (2 * rsz);
+  for (int i = tid; i < mr * n_chi; i += nt) {
+    const int b = i % n_chi, r = i / n_chi;
+    const double sv = ssorted[b];
+    const double inv = sv > 0.0 ? 1.0 / sv : 0.0;
+    site[r * chi + b] = cscale(L[r + order[b] * ldl], inv);
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// k_mixer: A[a,s',c] <- sum_s u[s',s] A[a,s,c], u = [[cos b, i sin b],[i sin b, cos b]]
+// (lib/dQA_utils.py:26-30 + lib/tenn.py:67-81 for a bond-1 MPO), all sites in one launch.
+// grid (N, batch)
+// ---------------------------------------------------------------------------------
+__global__ void k_mixer(DqaDev d, double cb, double sb) {
+  const int site = blockIdx.x, inst = blockIdx.y;
+  const int chi = d.chi;
+  const int* bond = d.bond + inst * (d.N + 1);
+  const int bl = bond[site], br = bond[site + 1];
+  cplx* a = d.mps + ((size_t)inst * d.N + site) * (size_t)(2 * chi * chi);
+  for (int i = threadIdx.x; i < bl * br; i += blockDim.x) {
+    const int c = i % br, r = i / br;
+    cplx* p0 = a + (r * 2 + 0) * chi + c;
+    cplx* p1 = a + (r * 2 + 1) * chi + c;
+    const cplx v0 = *p0, v1 = *p1;
+    // i*sb*v = (-sb*v.y, sb*v.x)
+    *p0 = cmk(cb * v0.x - sb * v1.y, cb * v0.y + sb * v1.x);
+    *p1 = cmk(cb * v1.x - sb * v0.y, cb * v1.y + sb * v0.x);
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// k_energy: T_{mu,k} = <psi| prod_i diag_s(exp(i pi k e[mu,i,s]/D)) |psi>, k = 0..D/2
+//   E'[b,d] = sum_s ph_s sum_{a,c} E[a,c] A[a,s,b] conj(A[c,s,d])   (lib/tenn.py:102-107)
+// grid (kh, n_xi, batch); shared: E, E2, W, As (chi*chi each)
+// n_phys_sites < N_sites supports the ancilla variant (lib/dQA_loss.py:28-46): trailing
+// sites carry the identity.
+// ---------------------------------------------------------------------------------
+__host__ __device__ inline size_t energy_smem(int chi) { return sizeof(cplx) * (size_t)4 * chi * chi; }
+
+__global__ void k_energy(DqaDev d) {
+  DQA_DYN_SMEM(smraw);
+  const int k = blockIdx.x, mu = blockIdx.y, inst = blockIdx.z, tid = threadIdx.x, nt = blockDim.x;
+  const int chi = d.chi;
+  const size_t rsz = (size_t)chi * chi;
+  cplx* E = (cplx*)smraw;
+  cplx* E2 = E + rsz;
+  cplx* W = E2 + rsz;
+  cplx* As = W + rsz;
+  const int* bond = d.bond + inst * (d.N + 1);
+  const uint8_t* hb = d.hbit + ((size_t)inst * d.n_xi + mu) * d.N;
+  const cplx wk = d.phase[k];  // exp(i pi q / D) with q = k*e, e = 2
+  if (tid == 0) E[0] = cmk(1.0, 0.0);
+  __syncthreads();
+  for (int i = 0; i < d.N; ++i) {
+    const int bl = bond[i], br = bond[i + 1];
+    const cplx* a = d.mps + ((size_t)inst * d.N + i) * (2 * rsz);
+    for (int s = 0; s < 2; ++s) {
+      for (int t = tid; t < bl * br; t += nt) {
+        const int b = t % br, r = t / br;
+        As[r * br + b] = a[(r * 2 + s) * chi + b];
+      }
+      __syncthreads();
+      // W[c,b] = sum_a E[a,c] A_s[a,b]
+      for (int t = tid; t < bl * br; t += nt) {
+        const int b = t % br, c = t / br;
+        cplx acc = cmk(0.0, 0.0);
+        for (int aa = 0; aa < bl; ++aa) acc = cfma(E[aa * bl + c], As[aa * br + b], acc);
+        W[c * br + b] = acc;
+      }
+      __syncthreads();
+      const cplx ph = (hb[i] ^ s) ? wk : cmk(1.0, 0.0);
+      // E2[b,dd] (+)= ph * sum_c W[c,b] conj(A_s[c,dd])
+      for (int t = tid; t < br * br; t += nt) {
+        const int dd = t % br, b = t / br;
+        cplx acc = cmk(0.0, 0.0);
+        for (int c = 0; c < bl; ++c) acc = cfmac(W[c * br + b], As[c * br + dd], acc);
+        acc = cmul(ph, acc);
+        E2[b * br + dd] = s ? cadd(E2[b * br + dd], acc) : acc;
+      }
+      __syncthreads();
+    }
+    cplx* t2 = E;
+    E = E2;
+    E2 = t2;
+  }
+  if (tid == 0) d.tmk[((size_t)inst * d.n_xi + mu) * d.kh + k] = E[0];
+}
+
+// eps = (1/N) sum_mu [ sum_{k<=D/2} g_k T_k + sum_{0<k<D/2} g_{D-k} conj(T_k) ]; one warp per instance
+__global__ void k_energy_reduce(DqaDev d, int slot) {
+  const int inst = blockIdx.x, lane = threadIdx.x;
+  cplx acc = cmk(0.0, 0.0);
+  const int n = d.n_xi * d.kh;
+  for (int i = lane; i < n; i += 32) {
+    const int k = i % d.kh;
+    const cplx t = d.tmk[(size_t)inst * n + i];
+    acc = cfma(d.gk[k], t, acc);
+    if (k > 0 && 2 * k != d.D) acc = cfmac(d.gk[d.D - k], t, acc);
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) d.eps[(size_t)inst * (d.P + 1) + slot] = cscale(acc, 1.0 / d.N);
+}

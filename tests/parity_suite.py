@@ -1,0 +1,135 @@
+"""Parity checks shared by the GPU tests (real libdqa.so through the C ABI) and the CPU
+emulator tests (same .cu sources under tests/emul).  `factory(N, n_xi, P, dt, chi, batch)`
+returns a perceptron_dqa_b200._lib.Plan."""
+import numpy as np
+
+import dqa_oracle as O
+from helpers import compare_states, golden, snapshots, unpack_mps
+
+
+def make(factory, g, batch=1, chi=None):
+    xi = g["xi"]
+    pl = factory(xi.shape[1], xi.shape[0], int(g["P"]), float(g["dt"]), int(chi or g["chi"]), batch)
+    pl.set_patterns(np.broadcast_to(xi, (batch,) + xi.shape))
+    pl.set_fourier(g["Uk_FT"], g["fxft"])
+    return pl
+
+
+def check_index_tensors(factory, name):
+    """P0: integer Hamming/phase index tensors bit-exact against the reference-derived fixture."""
+    g = golden(name)
+    pl = make(factory, g)
+    hbit, e, q = pl.index_tensors(0)
+    assert hbit.dtype == np.uint8 and e.dtype == np.int32 and q.dtype == np.int32
+    assert np.array_equal(hbit, g["hbit"])
+    assert np.array_equal(e.astype(np.int64), g["e"])
+    assert np.array_equal(q.astype(np.int64), g["q"])
+
+
+def check_eps0(factory, name):
+    g = golden(name)
+    pl = make(factory, g)
+    pl.reset_plus()
+    e0 = pl.eps_trace()[0, 0]
+    n, n_xi = g["xi"].shape[1], g["xi"].shape[0]
+    assert abs(e0 - O.eps0_closed_form(n, n_xi)) < 1e-14
+    assert abs(e0 - g["eps"][0]) < 1e-14
+    assert abs(e0.imag) < 1e-12
+
+
+def check_teacher_forced(factory, name, max_snaps=None):
+    """P1: load the reference's pre-sub-step MPS, run U_z + canonise + truncate on the device,
+    compare with the reference's post-sub-step state on gauge-invariant quantities."""
+    g = golden(name)
+    pl = make(factory, g)
+    worst = 0.0
+    for p, mu, pre, post in snapshots(g)[:max_snaps]:
+        pl.set_mps(pre, 0)
+        pl.apply_pattern(p, mu)
+        got = pl.get_mps(0)
+        fid = compare_states(got, post, g["xi"], g["fxft"])
+        worst = max(worst, abs(fid))
+        assert list(pl.bonds(0)) == [post[0].shape[0]] + [t.shape[2] for t in post]
+    assert not pl.status().any()
+    return worst
+
+
+def check_energy_on_snapshots(factory, name, max_snaps=3):
+    """compute_loss alone on reference states (a9)."""
+    g = golden(name)
+    pl = make(factory, g)
+    for _p, _mu, _pre, post in snapshots(g)[:max_snaps]:
+        pl.set_mps(post, 0)
+        got = pl.energy()[0]
+        want = O.compute_loss_fast(post, g["xi"], g["fxft"])
+        assert abs(got - want) < 1e-12, (got, want)
+        assert abs(got.imag) < 1e-12
+
+
+def check_mixer(factory, name):
+    """U_x alone on a reference state (a8): compare tensors elementwise (no gauge freedom)."""
+    g = golden(name)
+    pl = make(factory, g)
+    _p, _mu, _pre, post = snapshots(g)[0]
+    beta = 0.37
+    pl.set_mps(post, 0)
+    pl.apply_ux(beta)
+    got = pl.get_mps(0)
+    want = O.apply_mpsmpo(post, O.make_Ux(len(post), beta))
+    for a, b in zip(got, want):
+        assert np.abs(a - b).max() < 1e-15
+
+
+def check_free_run(factory, name, steps, tol=1e-10, envelope=None):
+    """P2: free-running trajectory against the reference fixture for the first `steps`
+    steps; beyond the point where the reference's own LAPACK-driver spread exceeds 1e-11 the
+    tolerance is max(1e-10, 10 x that spread)."""
+    g = golden(name)
+    pl = make(factory, g)
+    pl.reset_plus()
+    pl.step(steps)
+    eps = pl.eps_trace()[0, : steps + 1]
+    ref = g["eps"][: steps + 1]
+    diff = np.abs(eps - ref)
+    if envelope is not None:
+        spread = np.abs(golden(envelope)["eps"][: steps + 1] - ref)
+        bound = np.maximum(tol, 10.0 * np.maximum.accumulate(spread))
+    else:
+        bound = np.full(steps + 1, tol)
+    assert (diff <= bound).all(), (diff, bound)
+    bd = pl.bd_monitor()[0, : steps * g["xi"].shape[0]]
+    assert np.array_equal(bd, g["bd_monitor"][: len(bd)])
+    assert not pl.status().any()
+    return diff
+
+
+def check_final_state(factory, name, step):
+    """state after `step`+1 free-running steps vs the stored reference state."""
+    g = golden(name)
+    pl = make(factory, g)
+    pl.reset_plus()
+    pl.step(step + 1)
+    want = unpack_mps(g[f"state_after_step{step}_bonds"], g[f"state_after_step{step}_flat"])
+    compare_states(pl.get_mps(0), want, g["xi"], g["fxft"], tol_fid=1e-10, tol_eps=1e-10, tol_s=1e-10)
+
+
+def check_batch_consistency(factory, name, steps=2, batch=3):
+    """every instance of a batch evolves independently: identical patterns -> identical traces,
+    and a different pattern set in the middle slot does not disturb its neighbours."""
+    g = golden(name)
+    xi = g["xi"]
+    pl = factory(xi.shape[1], xi.shape[0], int(g["P"]), float(g["dt"]), int(g["chi"]), batch)
+    rng = np.random.default_rng(7)
+    other = (2 * rng.integers(0, 2, size=xi.shape) - 1).astype(np.int8)
+    pats = np.stack([xi if b != 1 else other for b in range(batch)])
+    pl.set_patterns(pats)
+    pl.set_fourier(g["Uk_FT"], g["fxft"])
+    pl.reset_plus()
+    pl.step(steps)
+    eps = pl.eps_trace()[:, : steps + 1]
+    assert np.abs(eps[0] - g["eps"][: steps + 1]).max() < 1e-11
+    assert np.array_equal(eps[0], eps[2])
+    ref = O.OracleDQA(other, int(g["P"]), float(g["dt"]), int(g["chi"]), fast_loss=True)
+    ref.init_fourier()
+    ref.run(steps=steps)
+    assert np.abs(eps[1] - np.array([l[1] for l in ref.loss])).max() < 1e-11

@@ -1,0 +1,51 @@
+"""CPU: the product's .cu sources compiled with g++ on the fiber SIMT emulator
+(tests/emul), checked against the reference-derived fixtures at small sizes.  This tests
+kernel *logic* (indexing, barriers, shuffles); the `-m gpu` tests are the parity tests
+proper.  The emulator library is never loaded by the package."""
+import pytest
+
+import parity_suite as ps
+
+
+@pytest.fixture(scope="module")
+def factory():
+    import emul_lib
+    from perceptron_dqa_b200._lib import Plan
+
+    lib = emul_lib.load()
+
+    def make(N, n_xi, P, dt, chi, batch):
+        return Plan(N, n_xi, P, dt, chi, batch=batch, lib=lib, workspace=emul_lib.numpy_workspace)
+
+    return make
+
+
+def test_index_tensors(factory):
+    ps.check_index_tensors(factory, "n7_chi4")
+    ps.check_index_tensors(factory, "c1_n12_chi10")
+
+
+def test_eps0(factory):
+    ps.check_eps0(factory, "n7_chi4")
+
+
+def test_teacher_forced_n7(factory):
+    ps.check_teacher_forced(factory, "n7_chi4")
+    ps.check_teacher_forced(factory, "n7_chi8_untruncated")
+
+
+def test_energy_and_mixer(factory):
+    ps.check_energy_on_snapshots(factory, "n7_chi4")
+    ps.check_mixer(factory, "n7_chi4")
+
+
+def test_free_run_n7(factory):
+    ps.check_free_run(factory, "n7_chi8_untruncated", steps=3)
+
+
+def test_batch(factory):
+    ps.check_batch_consistency(factory, "n7_chi4", steps=1, batch=3)
+
+
+def test_teacher_forced_n12_one_substep(factory):
+    ps.check_teacher_forced(factory, "c1_n12_chi10", max_snaps=1)

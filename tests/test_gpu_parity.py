@@ -1,0 +1,134 @@
+"""GPU: parity of libdqa.so (hand-written sm_100a kernels, called through the C ABI) against
+fixtures produced by the unmodified reference and against the numpy oracle.
+Protocol: SURVEY App. C (P0 integers bit-exact, P1 teacher-forced sub-steps to 1e-10 on
+gauge-invariant quantities, P2 free-running inside the reference's own envelope, P3
+untruncated regime, P4 known answers)."""
+import numpy as np
+import pytest
+
+import dqa_oracle as O
+import parity_suite as ps
+from helpers import golden
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def factory():
+    from perceptron_dqa_b200._lib import Plan
+
+    def make(N, n_xi, P, dt, chi, batch):
+        return Plan(N, n_xi, P, dt, chi, batch=batch)
+
+    return make
+
+
+@pytest.mark.parametrize("name", ["n7_chi4", "c1_n12_chi10", "c2_n21_chi10", "n15_chi10"])
+def test_p0_index_tensors_bit_exact(factory, name):
+    ps.check_index_tensors(factory, name)
+
+
+def test_p0_index_tensors_synthetic(factory):
+    """C4/C5 synthetic patterns: same integer formulas."""
+    for seed, shape in ((20230317, (17, 21)), (64, (51, 64))):
+        rng = np.random.default_rng(seed)
+        xi = (2 * rng.integers(0, 2, size=shape) - 1).astype(np.int8)
+        pl = factory(shape[1], shape[0], 4, 1.0, 4, 1)
+        pl.set_patterns(xi[None])
+        hbit, e, q = pl.index_tensors(0)
+        H, E, Q = O.hamming_tables(xi)
+        assert np.array_equal(hbit, H) and np.array_equal(e, E) and np.array_equal(q, Q)
+
+
+@pytest.mark.parametrize("name", ["n7_chi4", "c1_n12_chi10", "c2_n21_chi10", "n15_chi10"])
+def test_p4_eps0_known_answer(factory, name):
+    ps.check_eps0(factory, name)
+
+
+def test_p4_eps0_notebook_value(factory):
+    """quimb-dqa/quimb-dqa-demo.ipynb cell 21: eps(0) = 0.2930447289172962 for patterns_9-12."""
+    g = golden("c1_n12_chi10")
+    pl = ps.make(factory, g)
+    pl.reset_plus()
+    assert abs(pl.eps_trace()[0, 0].real - 0.2930447289172962) < 1e-14
+
+
+@pytest.mark.parametrize("name", ["n7_chi4", "n7_chi8_untruncated", "c1_n12_chi10", "c2_n21_chi10", "n15_chi10"])
+def test_p1_teacher_forced_substeps(factory, name):
+    ps.check_teacher_forced(factory, name)
+
+
+@pytest.mark.parametrize("name", ["n7_chi4", "c1_n12_chi10", "c2_n21_chi10"])
+def test_energy_and_mixer_on_reference_states(factory, name):
+    ps.check_energy_on_snapshots(factory, name)
+    ps.check_mixer(factory, name)
+
+
+def test_p3_untruncated_whole_trajectory(factory):
+    d = ps.check_free_run(factory, "n7_chi8_untruncated", steps=20, tol=1e-10)
+    g = golden("n7_chi8_untruncated")
+    sv = O.statevector_dqa(g["xi"], int(g["P"]), float(g["dt"]))
+    pl = ps.make(factory, g)
+    pl.reset_plus()
+    pl.step(20)
+    assert np.abs(pl.eps_trace()[0].real - sv).max() < 1e-6  # floor set by cutoff=1e-10
+    assert d.max() < 1e-10
+
+
+def test_p2_free_run_c1(factory):
+    ps.check_free_run(factory, "c1_n12_chi10", steps=40, envelope="c1_n12_chi10_gesvd")
+
+
+def test_p2_free_run_c2(factory):
+    ps.check_free_run(factory, "c2_n21_chi10", steps=20, envelope="c2_n21_chi10_gesvd")
+
+
+def test_p2_full_c1_envelope(factory):
+    """P=100 end to end: eps(1) inside the reference's own LAPACK-driver envelope
+    (reproducible to ~1e-4 absolute between gesdd and gesvd)."""
+    g = golden("c1_n12_chi10")
+    pl = ps.make(factory, g)
+    pl.reset_plus()
+    pl.step(100)
+    eps = pl.eps_trace()[0]
+    spread = np.abs(golden("c1_n12_chi10_gesvd")["eps"] - g["eps"])
+    assert abs(eps[-1] - g["eps"][-1]) < max(1e-10, 10 * spread.max())
+    assert np.abs(eps.imag).max() < 1e-12
+    assert not pl.status().any()
+
+
+def test_final_state_c1(factory):
+    ps.check_final_state(factory, "c1_n12_chi10", 5)
+
+
+def test_batch_independence(factory):
+    ps.check_batch_consistency(factory, "c1_n12_chi10", steps=2, batch=3)
+
+
+def test_driver_class_matches_fixture():
+    """The mydQA drop-in: construct -> init_fourier -> run -> loss[-1][1] (benchmarker-mps.py:32-43)."""
+    from perceptron_dqa_b200.dQA_mps import mydQA
+
+    g = golden("n7_chi4")
+    obj = mydQA(g["xi"], P=int(g["P"]), dt=float(g["dt"]), max_bond=int(g["chi"]))
+    obj.init_fourier()
+    assert np.abs(obj.Uk_FT - g["Uk_FT"]).max() == 0 and np.abs(obj.fxft - g["fxft"]).max() == 0
+    obj.run(skip_jit=4, print_info=False)
+    assert len(obj.loss) == int(g["P"]) + 1 and obj.loss[0][0] == 0
+    got = np.array([l[1] for l in obj.loss])
+    assert np.abs(got[:6] - g["eps"][:6]).max() < 1e-10
+    assert obj.bd_monitor == g["bd_monitor"].tolist()
+    assert abs(obj.compute_loss(obj.psi) - obj.loss[-1][1]) < 1e-12
+    assert obj.pp == int(g["P"])
+
+
+def test_errors_are_reported():
+    from perceptron_dqa_b200._lib import DqaError, Plan
+
+    pl = Plan(7, 5, 4, 1.0, 4)
+    with pytest.raises(DqaError):
+        pl.step(1)  # no patterns / tables
+    with pytest.raises(DqaError):
+        pl.set_patterns(np.zeros((1, 5, 7), dtype=np.int8))  # not +-1
+    with pytest.raises(DqaError):
+        Plan(7, 5, 4, 1.0, 400)  # chi beyond the shared-memory limit

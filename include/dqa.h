@@ -97,6 +97,15 @@ int dqa_energy(dqa_t* h, double* eps);
 int dqa_get_bonds(dqa_t* h, int inst, int32_t* bonds /* [N+1] */);
 int dqa_get_mps(dqa_t* h, int inst, int site, double* buf /* l*2*r complex */, int* l, int* r);
 int dqa_set_mps(dqa_t* h, int inst, int site, const double* buf, int l, int r);
+/* whole-batch state in the device layout: [batch][N][chi*2*chi] complex128 (site (a,s,c) at
+ * (a*2+s)*chi+c) followed by [batch][N+1] int32 bond dimensions.  For checkpoint/resume and
+ * for the end-to-end benchmark (pinned host buffers). */
+int dqa_state_bytes(const dqa_t* h, size_t* bytes);
+int dqa_download_state(dqa_t* h, void* host);
+int dqa_upload_state(dqa_t* h, const void* host);
+int dqa_sync(dqa_t* h);
+/* kernels launched by this handle so far */
+int dqa_get_launch_count(const dqa_t* h, int64_t* n);
 /* singular values seen at cut `bond` (between sites bond and bond+1) by the last truncation. */
 int dqa_get_schmidt(dqa_t* h, int inst, int bond, double* s /* [2*chi] */, int* n);
 

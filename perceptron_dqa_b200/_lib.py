@@ -57,6 +57,11 @@ _SIGS = {
     "dqa_get_bonds": ([_P, C.c_int, _P], C.c_int),
     "dqa_get_mps": ([_P, C.c_int, C.c_int, _P, C.POINTER(C.c_int), C.POINTER(C.c_int)], C.c_int),
     "dqa_set_mps": ([_P, C.c_int, C.c_int, _P, C.c_int, C.c_int], C.c_int),
+    "dqa_state_bytes": ([_P, C.POINTER(C.c_size_t)], C.c_int),
+    "dqa_download_state": ([_P, _P], C.c_int),
+    "dqa_upload_state": ([_P, _P], C.c_int),
+    "dqa_sync": ([_P], C.c_int),
+    "dqa_get_launch_count": ([_P, C.POINTER(C.c_int64)], C.c_int),
     "dqa_get_schmidt": ([_P, C.c_int, C.c_int, _P, C.POINTER(C.c_int)], C.c_int),
     "dqa_get_eps": ([_P, _P], C.c_int),
     "dqa_get_bd_monitor": ([_P, _P], C.c_int),
@@ -223,6 +228,25 @@ class Plan:
             t = np.ascontiguousarray(t, dtype=np.complex128)
             assert t.ndim == 3 and t.shape[1] == 2
             self._ck(self.lib.dqa_set_mps(self._h, inst, site, _ptr(t), t.shape[0], t.shape[2]))
+
+    def state_bytes(self):
+        v = C.c_size_t()
+        self._ck(self.lib.dqa_state_bytes(self._h, C.byref(v)))
+        return v.value
+
+    def download_state(self, host_ptr):
+        self._ck(self.lib.dqa_download_state(self._h, host_ptr))
+
+    def upload_state(self, host_ptr):
+        self._ck(self.lib.dqa_upload_state(self._h, host_ptr))
+
+    def sync(self):
+        self._ck(self.lib.dqa_sync(self._h))
+
+    def launch_count(self):
+        v = C.c_int64()
+        self._ck(self.lib.dqa_get_launch_count(self._h, C.byref(v)))
+        return v.value
 
     def schmidt(self, bond, inst=0):
         s = np.empty(2 * self.chi, dtype=np.float64)

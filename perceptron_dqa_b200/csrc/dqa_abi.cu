@@ -30,6 +30,7 @@ struct dqa_handle {
   struct Ev { int fam; cudaEvent_t a, b; };
   std::vector<Ev> evs;
   size_t ev_used;
+  long long launches;
 };
 
 static int fail(const dqa_t* h, int code, const char* fmt, ...) {
@@ -44,6 +45,8 @@ static int fail(const dqa_t* h, int code, const char* fmt, ...) {
     cudaError_t e_ = (call);                                                                             \
     if (e_ != cudaSuccess) return fail(h, (int)e_, "%s failed: %s", #call, cudaGetErrorString(e_)); \
   } while (0)
+
+#define HL(...) do { h->launches++; DQA_LAUNCH(__VA_ARGS__); } while (0)
 
 static size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
 
@@ -117,6 +120,7 @@ extern "C" int dqa_create(dqa_t** out, const dqa_config* cfg) {
   h->have_patterns = h->have_fourier = h->have_state = false;
   h->profiling = false;
   h->ev_used = 0;
+  h->launches = 0;
   DqaDev& d = h->dev;
   memset(&d, 0, sizeof(d));
   d.N = c.N;
@@ -198,7 +202,7 @@ extern "C" int dqa_set_patterns(dqa_t* h, const int8_t* xi) {
     if (xi[i] != 1 && xi[i] != -1) return fail(h, DQA_EINVAL, "pattern entry %zu is %d, not +-1", i, (int)xi[i]);
   CK(cudaMemcpyAsync(h->d_xi, xi, n, cudaMemcpyHostToDevice, h->stream));
   const int blocks = (int)((n + 255) / 256);
-  DQA_LAUNCH(k_hamming_tables, dim3(blocks < 1024 ? blocks : 1024), dim3(256), 0, h->stream, (const int8_t*)h->d_xi, (int)n,
+  HL(k_hamming_tables, dim3(blocks < 1024 ? blocks : 1024), dim3(256), 0, h->stream, (const int8_t*)h->d_xi, (int)n,
              h->dev.D, const_cast<uint8_t*>(h->dev.hbit), (int32_t*)nullptr, (int32_t*)nullptr);
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(h->stream));
@@ -215,7 +219,7 @@ extern "C" int dqa_get_index_tensors(dqa_t* h, int inst, uint8_t* hbit, int32_t*
   const int8_t* xi = h->d_xi + (size_t)inst * n;
   const int blocks = (int)((n + 127) / 128);
   // hbit is recomputed into the tail of d_q's scratch? no: reuse the plan's table for this instance
-  DQA_LAUNCH(k_hamming_tables, dim3(blocks), dim3(128), 0, h->stream, xi, (int)n, D, (uint8_t*)nullptr, h->d_e, h->d_q);
+  HL(k_hamming_tables, dim3(blocks), dim3(128), 0, h->stream, xi, (int)n, D, (uint8_t*)nullptr, h->d_e, h->d_q);
   CK(cudaGetLastError());
   if (hbit) CK(cudaMemcpyAsync(hbit, h->dev.hbit + (size_t)inst * n, n, cudaMemcpyDeviceToHost, h->stream));
   if (e) CK(cudaMemcpyAsync(e, h->d_e, n * 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
@@ -301,10 +305,10 @@ extern "C" int dqa_profile_end(dqa_t* h, double* ms, int64_t* launches) {
 // ---- launch sequences ------------------------------------------------------------------
 static int launch_canonize(dqa_t* h, int mu) {
   const DqaDev& d = h->dev;
-  DQA_LAUNCH(k_sector_init, dim3(d.batch), dim3(32), 0, h->stream, d);
+  HL(k_sector_init, dim3(d.batch), dim3(32), 0, h->stream, d);
   for (int n = d.N - 1; n >= 1; --n) {
     prof_a(h, 0);
-    DQA_LAUNCH(k_sector_qr, dim3(d.N - n + 1, d.batch), dim3(h->t_qr), sector_qr_smem(d.chi), h->stream, d, n, mu);
+    HL(k_sector_qr, dim3(d.N - n + 1, d.batch), dim3(h->t_qr), sector_qr_smem(d.chi), h->stream, d, n, mu);
     prof_b(h);
   }
   CK(cudaGetLastError());
@@ -314,16 +318,16 @@ static int launch_canonize(dqa_t* h, int mu) {
 static int launch_truncate(dqa_t* h, int p, int mu) {
   const DqaDev& d = h->dev;
   prof_a(h, 1);
-  DQA_LAUNCH(k_theta0, dim3(d.N, d.batch), dim3(64), 0, h->stream, d, mu, p);
+  HL(k_theta0, dim3(d.N, d.batch), dim3(64), 0, h->stream, d, mu, p);
   prof_b(h);
   for (int l = 0; l < d.N; ++l) {
     if (l > 0) {
       prof_a(h, 1);
-      DQA_LAUNCH(k_theta, dim3(d.N - l + 1, d.batch), dim3(h->t_theta), sizeof(cplx) * d.chi * d.chi, h->stream, d, l, mu);
+      HL(k_theta, dim3(d.N - l + 1, d.batch), dim3(h->t_theta), sizeof(cplx) * d.chi * d.chi, h->stream, d, l, mu);
       prof_b(h);
     }
     prof_a(h, 2);
-    DQA_LAUNCH(k_svd, dim3(d.batch), dim3(h->t_svd), svd_smem(d.chi), h->stream, d, l, mu, p);
+    HL(k_svd, dim3(d.batch), dim3(h->t_svd), svd_smem(d.chi), h->stream, d, l, mu, p);
     prof_b(h);
   }
   CK(cudaGetLastError());
@@ -333,8 +337,8 @@ static int launch_truncate(dqa_t* h, int p, int mu) {
 static int launch_energy(dqa_t* h, int slot) {
   const DqaDev& d = h->dev;
   prof_a(h, 4);
-  DQA_LAUNCH(k_energy, dim3(d.kh, d.n_xi, d.batch), dim3(h->t_energy), energy_smem(d.chi), h->stream, d);
-  DQA_LAUNCH(k_energy_reduce, dim3(d.batch), dim3(32), 0, h->stream, d, slot);
+  HL(k_energy, dim3(d.kh, d.n_xi, d.batch), dim3(h->t_energy), energy_smem(d.chi), h->stream, d);
+  HL(k_energy_reduce, dim3(d.batch), dim3(32), 0, h->stream, d, slot);
   prof_b(h);
   CK(cudaGetLastError());
   return DQA_OK;
@@ -349,7 +353,7 @@ extern "C" int dqa_reset_plus(dqa_t* h) {
   NEED_WS();
   if (!h->have_patterns || !h->have_fourier) return fail(h, DQA_ESTATE, "set patterns and Fourier tables first");
   const DqaDev& d = h->dev;
-  DQA_LAUNCH(k_init_plus, dim3(d.batch), dim3(256), 0, h->stream, d);
+  HL(k_init_plus, dim3(d.batch), dim3(256), 0, h->stream, d);
   CK(cudaMemsetAsync(d.counters, 0, sizeof(unsigned long long) * 4 * d.batch, h->stream));
   h->pp = 0;
   h->have_state = true;
@@ -388,7 +392,7 @@ extern "C" int dqa_apply_ux(dqa_t* h, double beta) {
   NEED_READY();
   const DqaDev& d = h->dev;
   prof_a(h, 3);
-  DQA_LAUNCH(k_mixer, dim3(d.N, d.batch), dim3(128), 0, h->stream, d, std::cos(beta), std::sin(beta));
+  HL(k_mixer, dim3(d.N, d.batch), dim3(128), 0, h->stream, d, std::cos(beta), std::sin(beta));
   prof_b(h);
   CK(cudaGetLastError());
   return DQA_OK;
@@ -534,6 +538,43 @@ extern "C" int dqa_get_counters(dqa_t* h, uint64_t* c, int reset) {
   return DQA_OK;
 }
 
+extern "C" int dqa_state_bytes(const dqa_t* h, size_t* bytes) {
+  if (!h || !bytes) return DQA_EINVAL;
+  const size_t B = h->cfg.batch, N = h->cfg.N, chi = h->cfg.chi;
+  *bytes = B * N * 2 * chi * chi * sizeof(cplx) + B * (N + 1) * sizeof(int);
+  return DQA_OK;
+}
+extern "C" int dqa_download_state(dqa_t* h, void* host) {
+  NEED_WS();
+  if (!host) return DQA_EINVAL;
+  const size_t B = h->cfg.batch, N = h->cfg.N, chi = h->cfg.chi;
+  const size_t nm = B * N * 2 * chi * chi * sizeof(cplx), nb = B * (N + 1) * sizeof(int);
+  CK(cudaMemcpyAsync(host, h->dev.mps, nm, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync((char*)host + nm, h->dev.bond, nb, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return DQA_OK;
+}
+extern "C" int dqa_upload_state(dqa_t* h, const void* host) {
+  NEED_WS();
+  if (!host) return DQA_EINVAL;
+  const size_t B = h->cfg.batch, N = h->cfg.N, chi = h->cfg.chi;
+  const size_t nm = B * N * 2 * chi * chi * sizeof(cplx), nb = B * (N + 1) * sizeof(int);
+  CK(cudaMemcpyAsync(h->dev.mps, host, nm, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->dev.bond, (const char*)host + nm, nb, cudaMemcpyHostToDevice, h->stream));
+  h->have_state = true;
+  return DQA_OK;
+}
+extern "C" int dqa_get_launch_count(const dqa_t* h, int64_t* n) {
+  if (!h || !n) return DQA_EINVAL;
+  *n = h->launches;
+  return DQA_OK;
+}
+extern "C" int dqa_sync(dqa_t* h) {
+  if (!h) return DQA_EINVAL;
+  CK(cudaStreamSynchronize(h->stream));
+  return DQA_OK;
+}
+
 // ---- ensemble moments (input of the one NCCL all-reduce) -------------------------------
 __global__ void k_ensemble_moments(DqaDev d, double* out) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
@@ -555,7 +596,7 @@ extern "C" int dqa_ensemble_moments(dqa_t* h, double* device_out) {
   NEED_WS();
   if (!device_out) return DQA_EINVAL;
   const int n = h->cfg.P + 1;
-  DQA_LAUNCH(k_ensemble_moments, dim3((n + 127) / 128), dim3(128), 0, h->stream, h->dev, device_out);
+  HL(k_ensemble_moments, dim3((n + 127) / 128), dim3(128), 0, h->stream, h->dev, device_out);
   CK(cudaGetLastError());
   return DQA_OK;
 }
@@ -590,7 +631,7 @@ extern "C" int dqa_measure_fp64_peak(dqa_t* h, double* tflops) {
   double best = 0.0;
   for (int rep = 0; rep < 4; ++rep) {
     CK(cudaEventRecord(a, h->stream));
-    DQA_LAUNCH(k_fp64_peak, dim3(blocks), dim3(threads), 0, h->stream, (double*)h->dev.work, iters);
+    HL(k_fp64_peak, dim3(blocks), dim3(threads), 0, h->stream, (double*)h->dev.work, iters);
     CK(cudaEventRecord(b, h->stream));
     CK(cudaEventSynchronize(b));
     float ms = 0.f;

@@ -89,7 +89,7 @@ static void carve(const dqa_config& c, DqaDev& d, Aux& aux, char* base, size_t* 
   d.eps = cv.take<cplx>(B * (P + 1));
   d.bdmon = cv.take<int>(B * P * nx);
   d.status = cv.take<int>(B);
-  d.counters = cv.take<unsigned long long>(B * 4);
+  d.counters = cv.take<unsigned long long>(B * 8);
   aux.d_xi = cv.take<int8_t>(B * nx * N);
   aux.d_e = cv.take<int32_t>(nx * N * 2);
   aux.d_q = cv.take<int32_t>(nx * N * 2 * D);
@@ -354,7 +354,7 @@ extern "C" int dqa_reset_plus(dqa_t* h) {
   if (!h->have_patterns || !h->have_fourier) return fail(h, DQA_ESTATE, "set patterns and Fourier tables first");
   const DqaDev& d = h->dev;
   HL(k_init_plus, dim3(d.batch), dim3(256), 0, h->stream, d);
-  CK(cudaMemsetAsync(d.counters, 0, sizeof(unsigned long long) * 4 * d.batch, h->stream));
+  CK(cudaMemsetAsync(d.counters, 0, sizeof(unsigned long long) * 8 * d.batch, h->stream));
   h->pp = 0;
   h->have_state = true;
   return launch_energy(h, 0);
@@ -532,8 +532,8 @@ extern "C" int dqa_get_status(dqa_t* h, int32_t* st) {
 extern "C" int dqa_get_counters(dqa_t* h, uint64_t* c, int reset) {
   NEED_WS();
   if (!c) return DQA_EINVAL;
-  CK(cudaMemcpyAsync(c, h->dev.counters, sizeof(uint64_t) * 4 * (size_t)h->cfg.batch, cudaMemcpyDeviceToHost, h->stream));
-  if (reset) CK(cudaMemsetAsync(h->dev.counters, 0, sizeof(uint64_t) * 4 * (size_t)h->cfg.batch, h->stream));
+  CK(cudaMemcpyAsync(c, h->dev.counters, sizeof(uint64_t) * 8 * (size_t)h->cfg.batch, cudaMemcpyDeviceToHost, h->stream));
+  if (reset) CK(cudaMemsetAsync(h->dev.counters, 0, sizeof(uint64_t) * 8 * (size_t)h->cfg.batch, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   return DQA_OK;
 }

@@ -108,7 +108,7 @@ struct DqaDev {
   cplx* eps;              // [batch][P+1]
   int* bdmon;             // [batch][P*n_xi]
   int* status;            // [batch]  bit0: non-finite, bit1: zero norm, bit2: Jacobi not converged
-  unsigned long long* counters;  // [batch][4] rotations, sweeps, svds, qr columns
+  unsigned long long* counters;  // [batch][8] rotations, sweeps, svds, qr columns, flops: LQ, Jacobi, sector QR, theta GEMMs
 };
 
 __host__ __device__ __forceinline__ int dqa_secbase(int N, int n) {

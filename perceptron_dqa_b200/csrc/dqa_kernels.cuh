@@ -223,7 +223,13 @@ __global__ void k_sector_qr(DqaDev d, int n, int mu) {
   }
   if (tid == 0) {
     d.qdim[((size_t)inst * (d.N + 1) + n) * d.smax + y] = q;
-    atomicAdd(&d.counters[inst * 4 + 3], (unsigned long long)q);
+    atomicAdd(&d.counters[inst * 8 + 3], (unsigned long long)q);
+    unsigned long long fl = (unsigned long long)m * bl * br * 8ull;  // M = R A^T
+    for (int k = 0; k < q; ++k) {
+      fl += 10ull * (m - k - 1) + 16ull * (unsigned long long)(bl - k - 1) * (m - k);   // zgeqr2 column k
+      fl += 6ull * (m - k - 1) + 16ull * (unsigned long long)(q - k - 1) * (m - k - 1);  // zung2r column k
+    }
+    atomicAdd(&d.counters[inst * 8 + 6], fl);
   }
 }
 
@@ -310,7 +316,9 @@ __global__ void k_theta(DqaDev d, int l, int mu) {
       for (int j = 0; j < qy; ++j) acc = cfma(C[b * qy + j], Q[(rowoff + jp) + j * ldq], acc);
       thc[(size_t)(b * 2 + s) * ld + offo + jp] = acc;
     }
+    if (tid == 0) atomicAdd(&d.counters[inst * 8 + 7], 8ull * cl * qo * qy);
   }
+  if (tid == 0) atomicAdd(&d.counters[inst * 8 + 7], 8ull * cl * qy * mrp);
 }
 
 // ---------------------------------------------------------------------------------
@@ -500,9 +508,14 @@ __global__ void k_svd(DqaDev d, int l, int mu, int p_step) {
     d.scale[inst] = sc;
     bond[l + 1] = n_chi;
     d.nsv[inst * d.N + l] = k;
-    atomicAdd(&d.counters[inst * 4 + 0], nrot_total);
-    atomicAdd(&d.counters[inst * 4 + 1], (unsigned long long)sweeps);
-    atomicAdd(&d.counters[inst * 4 + 2], 1ull);
+    atomicAdd(&d.counters[inst * 8 + 0], nrot_total);
+    atomicAdd(&d.counters[inst * 8 + 1], (unsigned long long)sweeps);
+    atomicAdd(&d.counters[inst * 8 + 2], 1ull);
+    unsigned long long lq = 0;
+    for (int kk = 0; kk < k; ++kk) lq += 10ull * (Q - kk - 1) + 16ull * (unsigned long long)(mr - kk - 1) * (Q - kk);
+    atomicAdd(&d.counters[inst * 8 + 4], lq);
+    atomicAdd(&d.counters[inst * 8 + 5],
+              (unsigned long long)sweeps * (unsigned long long)(k * (k - 1) / 2) * 16ull * mr + nrot_total * 20ull * mr);
     if (l == d.N - 1) d.bdmon[(size_t)inst * d.P * d.n_xi + (size_t)p_step * d.n_xi + mu] = bond[d.N / 2];
   }
   __syncthreads();

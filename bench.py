@@ -192,12 +192,6 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons, "samples": len(self.rows)}
 
 
-def svd_flops(cnt):
-    """FP64 flops the truncation kernel executed, from its own device counters:
-    [4] Householder-LQ flops, [5] Jacobi flops (dot products of every pair tested + rotations)."""
-    return float(cnt[4] + cnt[5])
-
-
 def run_ours(a):
     import torch
 
@@ -306,24 +300,36 @@ def run_ours(a):
     }
 
     if rank == 0 and not a.no_roofline:
-        # dominant kernel: k_svd (Householder LQ + one-sided Jacobi); FP64-bound
+        # per-kernel-family device time (CUDA events inside libdqa on the launching stream) and the
+        # FP64 flops each family executed (exact loop counts kept by the kernels themselves)
         pl.counters(reset=True)
         pl.profile_begin()
         pl.step(1)
         fam_ms, fam_n = pl.profile_end()
         cnt = pl.counters().sum(0).astype(np.float64)
         peak = pl.fp64_peak_tflops()
-        fl = svd_flops(cnt)
-        per_launch_ms = fam_ms["svd"] / max(1, fam_n["svd"])
-        achieved = fl / (fam_ms["svd"] * 1e-3) / 1e12 if fam_ms["svd"] > 0 else 0.0
+        bonds = pl.bonds(0)
+        e_fl = sum(16.0 * (bonds[i] ** 2 * bonds[i + 1] + bonds[i] * bonds[i + 1] ** 2) for i in range(a.n))
+        flops = {"jacobi": cnt[5], "lq": cnt[4], "sector_qr": cnt[6], "theta": cnt[7],
+                 "energy": float(e_fl) * a.nxi * (a.n // 2 + 1 + (a.n + 1) % 2 * 0) * B}
+        fams = {}
+        for f, fl in flops.items():
+            ms_f = fam_ms.get(f, 0.0)
+            ach = fl / (ms_f * 1e-3) / 1e12 if ms_f > 0 else 0.0
+            fams[f] = {"ms_per_step": ms_f, "launches": fam_n.get(f, 0), "flops_per_step": fl, "achieved_tflops": ach,
+                       "frac": ach / peak if peak else None, "share_of_step": ms_f / max(1e-9, sum(fam_ms.values()))}
+        dom = max(fams, key=lambda f: fams[f]["ms_per_step"])
         line["roofline"] = {
-            "kernel": "k_svd", "bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-            "frac": achieved / peak if peak else None, "traffic": None,
+            "kernel": {"jacobi": "k_jacobi", "lq": "k_lq", "sector_qr": "k_sector_qr", "theta": "k_theta", "energy": "k_energy"}[dom],
+            "bound": "fp64", "achieved": fams[dom]["achieved_tflops"], "peak": peak, "unit": "TFLOP/s",
+            "frac": fams[dom]["frac"], "traffic": None,
             "peak_source": "measured on this GPU by libdqa's DFMA probe (MEASURED_PEAKS.json has no FP64 entry; "
                            "B200 FP64 vector = FP64 tensor peak)",
-            "flops_per_launch": fl / max(1, fam_n["svd"]), "ms_per_launch": per_launch_ms,
-            "share_of_step": fam_ms["svd"] / max(1e-9, sum(fam_ms.values())),
-            "family_ms_per_step": fam_ms, "family_launches": fam_n,
+            "flops_per_launch": fams[dom]["flops_per_step"] / max(1, fams[dom]["launches"]),
+            "ms_per_launch": fams[dom]["ms_per_step"] / max(1, fams[dom]["launches"]),
+            "share_of_step": fams[dom]["share_of_step"], "families": fams,
+            "whole_step": {"flops": float(sum(flops.values())), "achieved_tflops": float(sum(flops.values())) / (sum(fam_ms.values()) * 1e-3) / 1e12,
+                           "frac": float(sum(flops.values())) / (sum(fam_ms.values()) * 1e-3) / 1e12 / peak if peak else None},
             "rotations_per_svd": float(cnt[0]) / max(1.0, float(cnt[2])), "sweeps_per_svd": float(cnt[1]) / max(1.0, float(cnt[2])),
         }
     if rank == 0 and B > 1:

@@ -113,8 +113,9 @@ int dqa_get_schmidt(dqa_t* h, int inst, int bond, double* s /* [2*chi] */, int* 
 int dqa_get_eps(dqa_t* h, double* eps /* [batch][P+1] complex */);
 int dqa_get_bd_monitor(dqa_t* h, int32_t* bd /* [batch][P*n_xi] */);
 int dqa_get_status(dqa_t* h, int32_t* status /* [batch] */);
-/* [batch][8] u64: Jacobi rotations, Jacobi sweeps, SVDs, QR columns, and the FP64 flops executed by
- * the Householder LQ, the Jacobi iteration, the sector QRs and the theta GEMMs (exact loop counts). */
+/* [batch][12] u64: Jacobi rotations, Jacobi sweeps, SVDs, QR columns, and the FP64 flops executed by
+ * the Householder LQ, the Jacobi iteration, the sector QRs and the theta GEMMs (exact loop counts),
+ * then SM cycles spent in the LQ and Jacobi phases of the truncation kernel (8, 9). */
 int dqa_get_counters(dqa_t* h, uint64_t* counters, int reset);
 
 /* ensemble moments for the multi-GPU reduction: writes to DEVICE memory (caller-owned,
@@ -123,8 +124,8 @@ int dqa_get_counters(dqa_t* h, uint64_t* counters, int reset);
 int dqa_ensemble_moments(dqa_t* h, double* device_out);
 
 /* profiling: per kernel-family device time, measured with CUDA events on the handle's
- * stream.  families: 0 sector_qr, 1 theta, 2 svd, 3 mixer, 4 energy. */
-#define DQA_NFAM 5
+ * stream.  families: 0 sector_qr, 1 theta, 2 lq, 3 mixer, 4 energy, 5 jacobi. */
+#define DQA_NFAM 6
 int dqa_profile_begin(dqa_t* h);
 int dqa_profile_end(dqa_t* h, double* ms /* [DQA_NFAM] */, int64_t* launches /* [DQA_NFAM] */);
 

@@ -13,8 +13,8 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libdqa.so")
-NFAM = 5
-FAMILIES = ("sector_qr", "theta", "svd", "mixer", "energy")
+NFAM = 6
+FAMILIES = ("sector_qr", "theta", "lq", "mixer", "energy", "jacobi")
 
 
 class DqaError(RuntimeError):
@@ -271,7 +271,7 @@ class Plan:
         return out
 
     def counters(self, reset=False):
-        out = np.empty((self.batch, 8), dtype=np.uint64)
+        out = np.empty((self.batch, 12), dtype=np.uint64)
         self._ck(self.lib.dqa_get_counters(self._h, _ptr(out), int(reset)))
         return out
 

@@ -9,6 +9,7 @@
 #include <complex>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -24,6 +25,7 @@ struct dqa_handle {
   int pp;
   bool have_patterns, have_fourier, have_state;
   int t_qr, t_theta, t_svd, t_energy;  // block sizes
+  int t_lq;
   char err[512];
   // profiling
   bool profiling;
@@ -82,6 +84,7 @@ static void carve(const dqa_config& c, DqaDev& d, Aux& aux, char* base, size_t* 
   d.qdim = cv.take<int>(B * (N + 1) * d.smax);
   d.theta = cv.take<cplx>(B * 2 * 2 * chi * (size_t)d.ld_theta);
   d.work = cv.take<cplx>(B * 2 * chi * (size_t)d.ld_theta);
+  d.lbuf = cv.take<cplx>(B * 4 * chi * chi);
   d.scale = cv.take<double>(B);
   d.schmidt = cv.take<double>(B * N * 2 * chi);
   d.nsv = cv.take<int>(B * N);
@@ -89,7 +92,7 @@ static void carve(const dqa_config& c, DqaDev& d, Aux& aux, char* base, size_t* 
   d.eps = cv.take<cplx>(B * (P + 1));
   d.bdmon = cv.take<int>(B * P * nx);
   d.status = cv.take<int>(B);
-  d.counters = cv.take<unsigned long long>(B * 8);
+  d.counters = cv.take<unsigned long long>(B * DQA_NCNT);
   aux.d_xi = cv.take<int8_t>(B * nx * N);
   aux.d_e = cv.take<int32_t>(nx * N * 2);
   aux.d_q = cv.take<int32_t>(nx * N * 2 * D);
@@ -111,7 +114,8 @@ extern "C" int dqa_create(dqa_t** out, const dqa_config* cfg) {
   *out = h;  // returned even on error so the message can be read; caller destroys it
   if (c.N < 2 || c.n_xi < 1 || c.P < 1 || c.chi < 1 || c.batch < 1) return fail(h, DQA_EINVAL, "N>=2, n_xi>=1, P>=1, chi>=1, batch>=1 required");
   if (c.N > 254) return fail(h, DQA_ELIMIT, "N=%d > 254 not supported", c.N);
-  if (sector_qr_smem(c.chi) > 227 * 1024 || svd_smem(c.chi) > 227 * 1024 || energy_smem(c.chi) > 227 * 1024)
+  if (sector_qr_smem(c.chi) > 227 * 1024 || svd_smem(c.chi) > 227 * 1024 || energy_smem(c.chi) > 227 * 1024 ||
+      lq_smem(((c.chi * (c.N + 1)) + 1) & ~1) > 227 * 1024)
     return fail(h, DQA_ELIMIT, "chi=%d needs more than 227 KB of shared memory per CTA in this build (max chi 48)", c.chi);
   h->stream = (cudaStream_t)c.stream;
   h->ws = nullptr;
@@ -137,16 +141,29 @@ extern "C" int dqa_create(dqa_t** out, const dqa_config* cfg) {
   d.cutoff = c.cutoff;
   // block sizes: warps scale with chi; the emulator build keeps them small
 #ifdef DQA_EMUL
-  h->t_qr = 64; h->t_theta = 64; h->t_svd = 64; h->t_energy = 64;
+  h->t_qr = 64; h->t_theta = 64; h->t_svd = 64; h->t_energy = 64; h->t_lq = 64;
 #else
   h->t_qr = c.chi <= 8 ? 128 : 256;
   h->t_theta = 256;
-  h->t_svd = c.chi <= 4 ? 128 : (c.chi <= 8 ? 256 : (c.chi <= 16 ? 512 : 1024));
+  {
+    // Jacobi: few warps per CTA, each owning ~8 column pairs per round; several CTAs share an SM
+    int warps = (c.chi + 7) / 8;
+    if (warps < 2) warps = 2;
+    if (warps > 8) warps = 8;
+    const char* env = getenv("DQA_JAC_WARPS");
+    if (env && atoi(env) >= 1 && atoi(env) <= 8) warps = atoi(env);
+    if (warps < (c.chi + 31) / 32) warps = (c.chi + 31) / 32;  // at most 32 column pairs per warp
+    h->t_svd = 32 * warps;
+    h->t_lq = c.chi <= 8 ? 128 : (c.chi <= 16 ? 256 : 512);
+    env = getenv("DQA_LQ_THREADS");
+    if (env && atoi(env) >= 32 && atoi(env) <= 1024) h->t_lq = atoi(env) & ~31;
+  }
   h->t_energy = c.chi <= 8 ? 64 : 256;
 #endif
   CK(cudaSetDevice(c.device));
   CK(cudaFuncSetAttribute(k_sector_qr, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sector_qr_smem(c.chi)));
-  CK(cudaFuncSetAttribute(k_svd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)svd_smem(c.chi)));
+  CK(cudaFuncSetAttribute(k_jacobi, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)svd_smem(c.chi)));
+  CK(cudaFuncSetAttribute(k_lq, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lq_smem(h->dev.ld_theta)));
   CK(cudaFuncSetAttribute(k_energy, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)energy_smem(c.chi)));
   CK(cudaFuncSetAttribute(k_theta, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(cplx) * c.chi * c.chi)));
   return DQA_OK;
@@ -327,7 +344,10 @@ static int launch_truncate(dqa_t* h, int p, int mu) {
       prof_b(h);
     }
     prof_a(h, 2);
-    HL(k_svd, dim3(d.batch), dim3(h->t_svd), svd_smem(d.chi), h->stream, d, l, mu, p);
+    HL(k_lq, dim3(d.batch), dim3(h->t_lq), lq_smem(d.ld_theta), h->stream, d, l);
+    prof_b(h);
+    prof_a(h, 5);
+    HL(k_jacobi, dim3(d.batch), dim3(h->t_svd), svd_smem(d.chi), h->stream, d, l, mu, p);
     prof_b(h);
   }
   CK(cudaGetLastError());
@@ -354,7 +374,7 @@ extern "C" int dqa_reset_plus(dqa_t* h) {
   if (!h->have_patterns || !h->have_fourier) return fail(h, DQA_ESTATE, "set patterns and Fourier tables first");
   const DqaDev& d = h->dev;
   HL(k_init_plus, dim3(d.batch), dim3(256), 0, h->stream, d);
-  CK(cudaMemsetAsync(d.counters, 0, sizeof(unsigned long long) * 8 * d.batch, h->stream));
+  CK(cudaMemsetAsync(d.counters, 0, sizeof(unsigned long long) * DQA_NCNT * d.batch, h->stream));
   h->pp = 0;
   h->have_state = true;
   return launch_energy(h, 0);
@@ -532,8 +552,8 @@ extern "C" int dqa_get_status(dqa_t* h, int32_t* st) {
 extern "C" int dqa_get_counters(dqa_t* h, uint64_t* c, int reset) {
   NEED_WS();
   if (!c) return DQA_EINVAL;
-  CK(cudaMemcpyAsync(c, h->dev.counters, sizeof(uint64_t) * 8 * (size_t)h->cfg.batch, cudaMemcpyDeviceToHost, h->stream));
-  if (reset) CK(cudaMemsetAsync(h->dev.counters, 0, sizeof(uint64_t) * 8 * (size_t)h->cfg.batch, h->stream));
+  CK(cudaMemcpyAsync(c, h->dev.counters, sizeof(uint64_t) * DQA_NCNT * (size_t)h->cfg.batch, cudaMemcpyDeviceToHost, h->stream));
+  if (reset) CK(cudaMemsetAsync(h->dev.counters, 0, sizeof(uint64_t) * DQA_NCNT * (size_t)h->cfg.batch, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   return DQA_OK;
 }

@@ -101,6 +101,7 @@ struct DqaDev {
   int* qdim;              // [batch][N+1][smax]            q_{n,y}
   cplx* theta;            // [batch][2][2chi*ld_theta]     Theta_l row-major, ping-pong on l
   cplx* work;             // [batch][2chi*ld_theta]        LQ scratch
+  cplx* lbuf;             // [batch][2chi*2chi]            L factor of Theta_l, col-major ld 2chi
   double* scale;          // [batch]                       renorm factor of the last truncation
   double* schmidt;        // [batch][N][2chi]              singular values seen at cut l
   int* nsv;               // [batch][N]
@@ -108,13 +109,15 @@ struct DqaDev {
   cplx* eps;              // [batch][P+1]
   int* bdmon;             // [batch][P*n_xi]
   int* status;            // [batch]  bit0: non-finite, bit1: zero norm, bit2: Jacobi not converged
-  unsigned long long* counters;  // [batch][8] rotations, sweeps, svds, qr columns, flops: LQ, Jacobi, sector QR, theta GEMMs
+  unsigned long long* counters;  // [batch][DQA_NCNT] rotations, sweeps, svds, qr columns, flops: LQ, Jacobi, sector QR, theta GEMMs; SM cycles: LQ, Jacobi
 };
 
 __host__ __device__ __forceinline__ int dqa_secbase(int N, int n) {
   // offset of site n's first Q block; site n (1..N-1) has sectors y = 0..N-n
   return (n - 1) * (N + 1) - (n - 1) * n / 2;
 }
+
+#define DQA_NCNT 12  // counters per instance
 
 enum {
   DQA_ST_NONFINITE = 1,

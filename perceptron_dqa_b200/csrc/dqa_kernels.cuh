@@ -223,13 +223,13 @@ __global__ void k_sector_qr(DqaDev d, int n, int mu) {
   }
   if (tid == 0) {
     d.qdim[((size_t)inst * (d.N + 1) + n) * d.smax + y] = q;
-    atomicAdd(&d.counters[inst * 8 + 3], (unsigned long long)q);
+    atomicAdd(&d.counters[inst * DQA_NCNT + 3], (unsigned long long)q);
     unsigned long long fl = (unsigned long long)m * bl * br * 8ull;  // M = R A^T
     for (int k = 0; k < q; ++k) {
       fl += 10ull * (m - k - 1) + 16ull * (unsigned long long)(bl - k - 1) * (m - k);   // zgeqr2 column k
       fl += 6ull * (m - k - 1) + 16ull * (unsigned long long)(q - k - 1) * (m - k - 1);  // zung2r column k
     }
-    atomicAdd(&d.counters[inst * 8 + 6], fl);
+    atomicAdd(&d.counters[inst * DQA_NCNT + 6], fl);
   }
 }
 
@@ -316,20 +316,191 @@ __global__ void k_theta(DqaDev d, int l, int mu) {
       for (int j = 0; j < qy; ++j) acc = cfma(C[b * qy + j], Q[(rowoff + jp) + j * ldq], acc);
       thc[(size_t)(b * 2 + s) * ld + offo + jp] = acc;
     }
-    if (tid == 0) atomicAdd(&d.counters[inst * 8 + 7], 8ull * cl * qo * qy);
+    if (tid == 0) atomicAdd(&d.counters[inst * DQA_NCNT + 7], 8ull * cl * qo * qy);
   }
-  if (tid == 0) atomicAdd(&d.counters[inst * 8 + 7], 8ull * cl * qy * mrp);
+  if (tid == 0) atomicAdd(&d.counters[inst * DQA_NCNT + 7], 8ull * cl * qy * mrp);
 }
 
 // ---------------------------------------------------------------------------------
-// k_svd: truncation at cut l for one instance (lib/tenn.py:229-252, :307-405).
-//   work <- Theta_l; Householder LQ (rows), L (mr x k) to shared; one-sided Jacobi on the
-//   columns of L (right rotations, one warp per column pair, round-robin ordering);
-//   sigma = column norms, sorted; trim rule; new site l = U_kept reshaped (c_l,2,n_chi).
-// shared: L (2chi x 2chi col-major) | sig, ssorted (2chi doubles each) | order (2chi ints) | red
+// k_lq: Householder LQ of Theta_l (mr x Q, row-major in global/L2) for one instance:
+//   Theta = L Qh, L (mr x k) lower-trapezoidal, k = min(mr, Q); only L is needed.
+// Blocked (compact WY) algorithm: a panel of LQ_PB rows is factored in shared memory, then
+// every trailing row is updated once per panel, Y <- Y - ((Y V) T) V^H, one warp per row,
+// lanes over columns; 2*PB complex FMAs per element and panel.
+// shared: Vp (PB x npad) | Tm (PB x PB) | Sg (PB x PB) | taus (PB)
+// ---------------------------------------------------------------------------------
+#define LQ_PB 8
+__host__ __device__ inline int lq_npad(int ncols) { return ((ncols + 7) & ~7) + 4; }
+__host__ __device__ inline size_t lq_smem(int ld_theta) {
+  return sizeof(cplx) * ((size_t)LQ_PB * lq_npad(ld_theta) + 2 * LQ_PB * LQ_PB + LQ_PB);
+}
+
+__global__ void __launch_bounds__(1024) k_lq(DqaDev d, int l) {
+  DQA_DYN_SMEM(smraw);
+  const int inst = blockIdx.x, tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarp = nt >> 5;
+  const int chi = d.chi, ld = d.ld_theta, npad = lq_npad(ld);
+  cplx* Vp = (cplx*)smraw;
+  cplx* Tm = Vp + (size_t)LQ_PB * npad;
+  cplx* Sg = Tm + LQ_PB * LQ_PB;
+  cplx* taus = Sg + LQ_PB * LQ_PB;
+  const int* bond = d.bond + inst * (d.N + 1);
+  const int mr = 2 * bond[l];
+  const int* qd1 = d.qdim + ((size_t)inst * (d.N + 1) + (l + 1)) * d.smax;
+  const int Q = qdim_prefix(qd1, d.N - l);
+  const int k = mr < Q ? mr : Q;
+  const cplx* th = d.theta + ((size_t)inst * 2 + (l & 1)) * (size_t)(2 * chi) * ld;
+  cplx* wk = d.work + (size_t)inst * (size_t)(2 * chi) * ld;
+  cplx* lout = d.lbuf + (size_t)inst * (size_t)(2 * chi) * (2 * chi);
+  const int ldl = 2 * chi;
+
+  for (int p0 = 0; p0 < k; p0 += LQ_PB) {
+    const int pb = (k - p0) < LQ_PB ? (k - p0) : LQ_PB;
+    const int n = Q - p0;  // panel columns p0..Q-1
+    const cplx* src = (p0 == 0) ? th : wk;
+    for (int i = tid; i < pb * n; i += nt) {
+      const int c = i % n, r = i / n;
+      Vp[r * npad + c] = src[(size_t)(p0 + r) * ld + p0 + c];
+    }
+    __syncthreads();
+    // ---- factor the panel (rows p0..p0+pb-1), unblocked, in shared memory ----
+    for (int i = 0; i < pb; ++i) {
+      cplx* row = Vp + i * npad;
+      if (warp == 0) {
+        double ss = 0.0;
+        for (int c = i + 1 + lane; c < n; c += 32) ss += cabs2(row[c]);
+        ss = warp_sum(ss);
+        const cplx alpha = row[i];
+        double beta;
+        cplx t, scal;
+        householder_gen(cconj(alpha), ss, beta, t, scal);
+        const cplx cs = cconj(scal);  // stored vector is conj(v)
+        __syncwarp();
+        for (int c = i + 1 + lane; c < n; c += 32) row[c] = cmul(row[c], cs);
+        if (lane == 0) {
+          taus[i] = t;
+          row[i] = cmk(beta, 0.0);
+        }
+      }
+      __syncthreads();
+      const cplx t = taus[i];
+      if (t.x != 0.0 || t.y != 0.0) {
+        for (int r = i + 1 + warp; r < pb; r += nwarp) {
+          cplx* yr = Vp + r * npad;
+          cplx w = (lane == 0) ? yr[i] : cmk(0.0, 0.0);
+          for (int c = i + 1 + lane; c < n; c += 32) w = cfmac(yr[c], row[c], w);
+          w = warp_sum(w);
+          const cplx tw = cmul(t, w);
+          if (lane == 0) yr[i] = csub(yr[i], tw);
+          for (int c = i + 1 + lane; c < n; c += 32) yr[c] = cfms(tw, row[c], yr[c]);
+        }
+      }
+      __syncthreads();
+    }
+    // ---- L entries of the panel rows go back to the work buffer; Vp becomes the clean V ----
+    for (int i = tid; i < pb * pb; i += nt) {
+      const int c = i % pb, r = i / pb;
+      if (c <= r) {
+        wk[(size_t)(p0 + r) * ld + p0 + c] = Vp[r * npad + c];
+      }
+    }
+    __syncthreads();
+    for (int i = tid; i < pb * pb; i += nt) {
+      const int c = i % pb, r = i / pb;
+      if (c < r) Vp[r * npad + c] = cmk(0.0, 0.0);
+      if (c == r) Vp[r * npad + c] = cmk(1.0, 0.0);
+    }
+    __syncthreads();
+    const int r_first = p0 + pb;
+    if (r_first < mr) {
+      // ---- T of the compact WY form: H_1...H_pb = I - V T V^H ----
+      const int ntask = pb * (pb - 1) / 2;
+      for (int task = warp; task < ntask; task += nwarp) {
+        int i = 1, acc = 0;
+        while (acc + i <= task) {
+          acc += i;
+          ++i;
+        }
+        const int j = task - acc;  // j < i
+        const cplx* vj = Vp + j * npad;
+        const cplx* vi = Vp + i * npad;
+        cplx sacc = cmk(0.0, 0.0);
+        for (int c = i + lane; c < n; c += 32) sacc = cfmac(vj[c], vi[c], sacc);  // v_j^H v_i
+        sacc = warp_sum(sacc);
+        if (lane == 0) Sg[j * LQ_PB + i] = sacc;
+      }
+      __syncthreads();
+      if (tid == 0) {
+        for (int i = 0; i < pb; ++i) {
+          const cplx ti = taus[i];
+          for (int j = 0; j < i; ++j) {
+            cplx acc = cmk(0.0, 0.0);
+            for (int m = j; m < i; ++m) acc = cfma(Tm[j * LQ_PB + m], Sg[m * LQ_PB + i], acc);
+            Tm[j * LQ_PB + i] = cmul(cmk(-ti.x, -ti.y), acc);
+          }
+          Tm[i * LQ_PB + i] = ti;
+        }
+      }
+      __syncthreads();
+      // ---- trailing rows: one warp per row ----
+      for (int r = r_first + warp; r < mr; r += nwarp) {
+        const cplx* ysrc = src + (size_t)r * ld + p0;
+        cplx* ydst = wk + (size_t)r * ld + p0;
+        cplx acc[LQ_PB];
+#pragma unroll
+        for (int i = 0; i < LQ_PB; ++i) acc[i] = cmk(0.0, 0.0);
+        for (int c = lane; c < n; c += 32) {
+          const cplx y = ysrc[c];
+#pragma unroll
+          for (int i = 0; i < LQ_PB; ++i)
+            if (i < pb) acc[i] = cfmac(y, Vp[i * npad + c], acc[i]);  // y * conj(vbar_i) = (Y V)_i
+        }
+#pragma unroll
+        for (int i = 0; i < LQ_PB; ++i) acc[i] = warp_sum(acc[i]);
+        // Z = W T : lane i computes Z_i
+        cplx zme = cmk(0.0, 0.0);
+#pragma unroll
+        for (int j = 0; j < LQ_PB; ++j)
+          if (j < pb && lane < pb && j <= lane) zme = cfma(acc[j], Tm[j * LQ_PB + lane], zme);
+        cplx z[LQ_PB];
+#pragma unroll
+        for (int i = 0; i < LQ_PB; ++i) {
+          z[i].x = __shfl_sync(DQA_FULL, zme.x, i);
+          z[i].y = __shfl_sync(DQA_FULL, zme.y, i);
+        }
+        for (int c = lane; c < n; c += 32) {
+          cplx y = ysrc[c];
+#pragma unroll
+          for (int i = 0; i < LQ_PB; ++i)
+            if (i < pb) y = cfms(z[i], Vp[i * npad + c], y);
+          ydst[c] = y;
+        }
+      }
+    }
+    __syncthreads();
+  }
+  for (int i = tid; i < mr * k; i += nt) {
+    const int r = i % mr, c = i / mr;
+    lout[r + c * ldl] = (c <= r) ? wk[(size_t)r * ld + c] : cmk(0.0, 0.0);
+  }
+  if (tid == 0) {
+    unsigned long long lq = 0;
+    for (int kk = 0; kk < k; ++kk) lq += 10ull * (Q - kk - 1) + 16ull * (unsigned long long)(mr - kk - 1) * (Q - kk);
+    atomicAdd(&d.counters[inst * DQA_NCNT + 4], lq);
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// k_jacobi: SVD of L (mr x k) by one-sided Jacobi + the reference's trim rule
+// (lib/tenn.py:317-354) + the new left-orthonormal site tensor (lib/tenn.py:229-252).
+// Few warps per CTA (several CTAs share an SM): every warp owns ppw column pairs per round;
+// the complex dot products are reduced with warp shuffles; the rotation parameters of the
+// warp's pairs are computed lane-parallel (lane u <-> pair u) and broadcast with shuffles,
+// so the scalar FP64 chain is paid once per warp and round, not once per pair.
+// Squared column norms are cached (exact recomputation every sweep).
+// shared: L (2chi x 2chi col-major, ld = mr) | nrm2/sig, ssorted (2chi doubles) | order | sh_i
 // ---------------------------------------------------------------------------------
 __host__ __device__ inline size_t svd_smem(int chi) {
-  return sizeof(cplx) * (size_t)(2 * chi) * (2 * chi) + sizeof(double) * (4 * chi + 64) + sizeof(int) * (2 * chi + 8);
+  return sizeof(cplx) * (size_t)(2 * chi) * (2 * chi) + sizeof(double) * (4 * chi + 8) + sizeof(int) * (2 * chi + 8);
 }
 
 __device__ __forceinline__ void rr_pair(int n, int round, int idx, int& p, int& q) {
@@ -338,8 +509,10 @@ __device__ __forceinline__ void rr_pair(int n, int round, int idx, int& p, int& 
     p = n - 1;
     q = round;
   } else {
-    p = (round + idx) % (n - 1);
-    q = (round - idx + (n - 1)) % (n - 1);
+    p = round + idx;
+    if (p >= n - 1) p -= n - 1;
+    q = round - idx;
+    if (q < 0) q += n - 1;
   }
   if (p > q) {
     const int t = p;
@@ -348,110 +521,113 @@ __device__ __forceinline__ void rr_pair(int n, int round, int idx, int& p, int& 
   }
 }
 
-__global__ void k_svd(DqaDev d, int l, int mu, int p_step) {
+#define JAC_UN 4
+__global__ void __launch_bounds__(256) k_jacobi(DqaDev d, int l, int mu, int p_step) {
   DQA_DYN_SMEM(smraw);
   const int inst = blockIdx.x, tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarp = nt >> 5;
-  const int chi = d.chi, ld = d.ld_theta;
+  const int chi = d.chi;
   const size_t rsz = (size_t)chi * chi;
   cplx* L = (cplx*)smraw;
   double* sig = (double*)(L + (size_t)(2 * chi) * (2 * chi));
   double* ssorted = sig + 2 * chi;
-  double* red = ssorted + 2 * chi;  // 64 doubles
-  int* order = (int*)(red + 64);
+  int* order = (int*)(ssorted + 2 * chi + 8);
   int* sh_i = order + 2 * chi;  // [0]=rotation count, [1]=n_chi
   int* bond = d.bond + inst * (d.N + 1);
   const int mr = 2 * bond[l];
   const int* qd1 = d.qdim + ((size_t)inst * (d.N + 1) + (l + 1)) * d.smax;
-  const int Q = qdim_prefix(qd1, d.N - l);  // sectors 0..N-l-1
+  const int Q = qdim_prefix(qd1, d.N - l);
   const int k = mr < Q ? mr : Q;
   const int ldl = mr;
-  const cplx* th = d.theta + ((size_t)inst * 2 + (l & 1)) * (size_t)(2 * chi) * ld;
-  cplx* wk = d.work + (size_t)inst * (size_t)(2 * chi) * ld;
-
-  for (int i = tid; i < mr * Q; i += nt) {
-    const int c = i % Q, r = i / Q;
-    wk[(size_t)r * ld + c] = th[(size_t)r * ld + c];
-  }
-  __syncthreads();
-
-  // ---- Householder LQ on rows of wk ------------------------------------------------
-  for (int kk = 0; kk < k; ++kk) {
-    cplx* row = wk + (size_t)kk * ld;
-    double ss = 0.0;
-    for (int j = kk + 1 + tid; j < Q; j += nt) ss += cabs2(row[j]);
-    const cplx alpha = row[kk];
-    ss = block_sum(ss, red);
-    double beta;
-    cplx t, scal;
-    householder_gen(cconj(alpha), ss, beta, t, scal);
-    // v = conj(x[1:])*scal  ->  stored conj(v) = x[1:] * conj(scal)
-    const cplx cs = cconj(scal);
-    for (int j = kk + 1 + tid; j < Q; j += nt) row[j] = cmul(row[j], cs);
-    __syncthreads();
-    if (tid == 0) row[kk] = cmk(beta, 0.0);
-    if (t.x != 0.0 || t.y != 0.0) {
-      for (int r = kk + 1 + warp; r < mr; r += nwarp) {
-        cplx* yr = wk + (size_t)r * ld;
-        cplx w = (lane == 0) ? yr[kk] : cmk(0.0, 0.0);
-        for (int j = kk + 1 + lane; j < Q; j += 32) w = cfmac(yr[j], row[j], w);  // y_j * conj(vbar_j)
-        w = warp_sum(w);
-        const cplx tw = cmul(t, w);
-        if (lane == 0) yr[kk] = csub(yr[kk], tw);
-        for (int j = kk + 1 + lane; j < Q; j += 32) yr[j] = cfms(tw, row[j], yr[j]);
-      }
-    }
-    __syncthreads();
-  }
+  const cplx* lin = d.lbuf + (size_t)inst * (size_t)(2 * chi) * (2 * chi);
   for (int i = tid; i < mr * k; i += nt) {
     const int r = i % mr, c = i / mr;
-    L[r + c * ldl] = (c <= r) ? wk[(size_t)r * ld + c] : cmk(0.0, 0.0);
+    L[r + c * ldl] = lin[r + c * (2 * chi)];
   }
   __syncthreads();
 
-  // ---- one-sided Jacobi on the columns of L ----------------------------------------
-  const int kp = k + (k & 1);
-  const double tol = sqrt((double)mr) * 2.220446049250313e-16;
+  // Work decomposition: a warp is 4 groups of 8 lanes; one group owns one column pair per
+  // pass (8 lanes x mr/8 rows each), so a warp orthogonalises 4 pairs per pass with 3-stage
+  // shuffle reductions that all four groups share.
+  const int kp = k + (k & 1), half = kp >> 1;
+  const int ppw = (half + nwarp - 1) / nwarp;  // pairs per warp and round
+  const int grp = lane >> 3, li = lane & 7;
+  const double tol = sqrt((double)mr) * 2.220446049250313e-16, tol2 = tol * tol;
+  double* nrm2 = sig;
   int sweeps = 0, converged = (k <= 1);
   unsigned long long nrot_total = 0;
   for (int sweep = 0; sweep < d.max_sweeps && !converged; ++sweep) {
+    for (int j0 = warp * 4; j0 < k; j0 += nwarp * 4) {  // warp-uniform trip count
+      const int j = j0 + grp;
+      double a = 0.0;
+      if (j < k)
+        for (int r = li; r < mr; r += 8) a += cabs2(L[r + j * ldl]);
+      a += __shfl_xor_sync(DQA_FULL, a, 4);
+      a += __shfl_xor_sync(DQA_FULL, a, 2);
+      a += __shfl_xor_sync(DQA_FULL, a, 1);
+      if (li == 0 && j < k) nrm2[j] = a;
+    }
     if (tid == 0) sh_i[0] = 0;
     __syncthreads();
+    int myrot = 0;
     for (int round = 0; round < kp - 1; ++round) {
-      for (int pr = warp; pr < kp / 2; pr += nwarp) {
-        int p, q;
-        rr_pair(kp, round, pr, p, q);
-        if (q >= k) continue;  // padded dummy column (warp-uniform)
+      for (int u0 = 0; u0 < ppw; u0 += 4) {
+        const int pr = warp * ppw + u0 + grp;
+        int p = 0, q = 0;
+        bool act = (u0 + grp < ppw) && (pr < half);
+        if (act) {
+          rr_pair(kp, round, pr, p, q);
+          act = q < k;  // padded dummy column
+        }
         cplx* xp = L + p * ldl;
         cplx* xq = L + q * ldl;
         double a = 0.0, b = 0.0;
         cplx g = cmk(0.0, 0.0);
-        for (int r = lane; r < mr; r += 32) {
-          const cplx vp = xp[r], vq = xq[r];
-          a += cabs2(vp);
-          b += cabs2(vq);
-          g = cfmac(vq, vp, g);  // conj(xp) * xq
+        if (act) {
+          a = nrm2[p];
+          b = nrm2[q];
+          for (int r = li; r < mr; r += 8) g = cfmac(xq[r], xp[r], g);  // conj(xp) * xq
         }
-        a = warp_sum(a);
-        b = warp_sum(b);
-        g = warp_sum(g);
-        const double ag = sqrt(cabs2(g));
-        if (ag > tol * sqrt(a * b) && ag > 0.0) {
-          const double zeta = (b - a) / (2.0 * ag);
-          const double tt = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-          const double c = 1.0 / sqrt(1.0 + tt * tt);
-          const double s = c * tt;
-          const cplx ph = cmk(g.x / ag, -g.y / ag);  // e^{-i phi}
-          const cplx sph = cscale(ph, s), cph = cscale(ph, c);
-          for (int r = lane; r < mr; r += 32) {
-            const cplx vp = xp[r], vq = xq[r];
-            xp[r] = cfms(sph, vq, cscale(vp, c));  // c*xp - s e^{-i phi} xq
-            xq[r] = cfma(cph, vq, cscale(vp, s));  // s*xp + c e^{-i phi} xq
+        g.x += __shfl_xor_sync(DQA_FULL, g.x, 4);
+        g.y += __shfl_xor_sync(DQA_FULL, g.y, 4);
+        g.x += __shfl_xor_sync(DQA_FULL, g.x, 2);
+        g.y += __shfl_xor_sync(DQA_FULL, g.y, 2);
+        g.x += __shfl_xor_sync(DQA_FULL, g.x, 1);
+        g.y += __shfl_xor_sync(DQA_FULL, g.y, 1);
+        const double ag2 = cabs2(g);
+        if (act && ag2 > tol2 * a * b && ag2 > 0.0) {
+          const double rinv = rsqrt(ag2);
+          const double ag = ag2 * rinv;
+          const double zeta = 0.5 * (b - a) * rinv;
+          const double az = fabs(zeta);
+          double tt;
+          if (az < 1e100) {
+            const double w = fma(zeta, zeta, 1.0);
+            tt = 1.0 / (az + w * rsqrt(w));
+          } else {
+            tt = 0.5 / az;
           }
-          if (lane == 0) atomicAdd(&sh_i[0], 1);
+          tt = copysign(tt, zeta);
+          const double c = rsqrt(fma(tt, tt, 1.0));
+          const double sn = c * tt;
+          const cplx ph = cmk(g.x * rinv, -g.y * rinv);  // e^{-i phi}
+          const cplx sph = cscale(ph, sn), cph = cscale(ph, c);
+          for (int r = li; r < mr; r += 8) {
+            const cplx vp = xp[r], vq = xq[r];
+            xp[r] = cfms(sph, vq, cscale(vp, c));   // c*xp - s e^{-i phi} xq
+            xq[r] = cfma(cph, vq, cscale(vp, sn));  // s*xp + c e^{-i phi} xq
+          }
+          if (li == 0) {
+            const double na = a - tt * ag, nb = b + tt * ag;
+            nrm2[p] = na > 0.0 ? na : 0.0;
+            nrm2[q] = nb > 0.0 ? nb : 0.0;
+            myrot++;
+          }
         }
       }
       __syncthreads();
     }
+    if (myrot) atomicAdd(&sh_i[0], myrot);
+    __syncthreads();
     sweeps++;
     nrot_total += (unsigned long long)sh_i[0];
     converged = (sh_i[0] == 0);
@@ -508,14 +684,12 @@ __global__ void k_svd(DqaDev d, int l, int mu, int p_step) {
     d.scale[inst] = sc;
     bond[l + 1] = n_chi;
     d.nsv[inst * d.N + l] = k;
-    atomicAdd(&d.counters[inst * 8 + 0], nrot_total);
-    atomicAdd(&d.counters[inst * 8 + 1], (unsigned long long)sweeps);
-    atomicAdd(&d.counters[inst * 8 + 2], 1ull);
-    unsigned long long lq = 0;
-    for (int kk = 0; kk < k; ++kk) lq += 10ull * (Q - kk - 1) + 16ull * (unsigned long long)(mr - kk - 1) * (Q - kk);
-    atomicAdd(&d.counters[inst * 8 + 4], lq);
-    atomicAdd(&d.counters[inst * 8 + 5],
-              (unsigned long long)sweeps * (unsigned long long)(k * (k - 1) / 2) * 16ull * mr + nrot_total * 20ull * mr);
+    atomicAdd(&d.counters[inst * DQA_NCNT + 0], nrot_total);
+    atomicAdd(&d.counters[inst * DQA_NCNT + 1], (unsigned long long)sweeps);
+    atomicAdd(&d.counters[inst * DQA_NCNT + 2], 1ull);
+    atomicAdd(&d.counters[inst * DQA_NCNT + 5],
+              (unsigned long long)sweeps * (unsigned long long)(k * (k - 1) / 2) * 8ull * mr + nrot_total * 20ull * mr +
+                  (unsigned long long)sweeps * 4ull * mr * k);
     if (l == d.N - 1) d.bdmon[(size_t)inst * d.P * d.n_xi + (size_t)p_step * d.n_xi + mu] = bond[d.N / 2];
   }
   __syncthreads();

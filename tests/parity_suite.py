@@ -121,7 +121,8 @@ def check_free_run(factory, name, steps, tol=1e-10, use_envelope=False):
         bound = np.maximum(tol, 10.0 * reference_envelope(name, steps))
     else:
         bound = np.full(steps + 1, tol)
-    assert (diff <= bound).all(), (diff, bound)
+    worst = int(np.argmax(diff / bound))
+    assert (diff <= bound).all(), f"step {worst}: |d eps|={diff[worst]:.3e} > bound {bound[worst]:.3e}; diffs={np.array2string(diff, precision=1)}; bounds={np.array2string(bound, precision=1)}"
     bd = pl.bd_monitor()[0, : steps * g["xi"].shape[0]]
     assert np.array_equal(bd, g["bd_monitor"][: len(bd)])
     assert not pl.status().any()

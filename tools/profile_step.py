@@ -48,7 +48,7 @@ def main():
     out = dict(cfg=vars(a), warm_s=t1 - t0, ms_per_step={k: v / a.steps for k, v in ms.items()}, launches=n,
                wall_s_per_step_profiled=(t2 - t1) / a.steps, wall_s_per_step=(t3 - t2) / a.steps,
                rotations_per_svd=float(cnt[0]) / max(1, int(cnt[2])), sweeps_per_svd=float(cnt[1]) / max(1, int(cnt[2])),
-               bonds=pl.bonds(0).tolist(), fp64_peak_tflops=pl.fp64_peak_tflops())
+               bonds=pl.bonds(0).tolist(),                flops_per_step_per_inst={k: float(cnt[i]) / a.steps / a.batch for k, i in (('lq', 4), ('jacobi', 5), ('sector_qr', 6), ('theta', 7))}, fp64_peak_tflops=pl.fp64_peak_tflops())
     print(json.dumps(out))
 
 

@@ -141,9 +141,11 @@ extern "C" int dqa_create(dqa_t** out, const dqa_config* cfg) {
   d.cutoff = c.cutoff;
   // block sizes: warps scale with chi; the emulator build keeps them small
 #ifdef DQA_EMUL
-  h->t_qr = 64; h->t_theta = 64; h->t_svd = 64; h->t_energy = 64; h->t_lq = 64;
+  h->t_qr = 32 * ((8 * c.chi + 31) / 32); h->t_theta = 64; h->t_svd = 64; h->t_energy = 64; h->t_lq = 64;
+  if (h->t_qr < 64) h->t_qr = 64;
 #else
-  h->t_qr = c.chi <= 8 ? 128 : 256;
+  h->t_qr = 32 * ((8 * c.chi + 31) / 32);  // one 8-lane group per column of the sector block
+  if (h->t_qr < 64) h->t_qr = 64;
   h->t_theta = 256;
   {
     // Jacobi: few warps per CTA, each owning ~8 column pairs per round; several CTAs share an SM
@@ -161,7 +163,10 @@ extern "C" int dqa_create(dqa_t** out, const dqa_config* cfg) {
   h->t_energy = c.chi <= 8 ? 64 : 256;
 #endif
   CK(cudaSetDevice(c.device));
-  CK(cudaFuncSetAttribute(k_sector_qr, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sector_qr_smem(c.chi)));
+  CK(cudaFuncSetAttribute(k_sector_qr<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sector_qr_smem(c.chi)));
+  CK(cudaFuncSetAttribute(k_sector_qr<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sector_qr_smem(c.chi)));
+  CK(cudaFuncSetAttribute(k_sector_qr<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sector_qr_smem(c.chi)));
+  CK(cudaFuncSetAttribute(k_sector_qr<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sector_qr_smem(c.chi)));
   CK(cudaFuncSetAttribute(k_jacobi, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)svd_smem(c.chi)));
   CK(cudaFuncSetAttribute(k_lq, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lq_smem(h->dev.ld_theta)));
   CK(cudaFuncSetAttribute(k_energy, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)energy_smem(c.chi)));
@@ -325,7 +330,12 @@ static int launch_canonize(dqa_t* h, int mu) {
   HL(k_sector_init, dim3(d.batch), dim3(32), 0, h->stream, d);
   for (int n = d.N - 1; n >= 1; --n) {
     prof_a(h, 0);
-    HL(k_sector_qr, dim3(d.N - n + 1, d.batch), dim3(h->t_qr), sector_qr_smem(d.chi), h->stream, d, n, mu);
+    const dim3 grid(d.N - n + 1, d.batch), block(h->t_qr);
+    const size_t sm = sector_qr_smem(d.chi);
+    if (d.chi <= 8) HL(k_sector_qr<2>, grid, block, sm, h->stream, d, n, mu);
+    else if (d.chi <= 16) HL(k_sector_qr<4>, grid, block, sm, h->stream, d, n, mu);
+    else if (d.chi <= 32) HL(k_sector_qr<8>, grid, block, sm, h->stream, d, n, mu);
+    else HL(k_sector_qr<12>, grid, block, sm, h->stream, d, n, mu);
     prof_b(h);
   }
   CK(cudaGetLastError());

@@ -79,6 +79,45 @@ __device__ __forceinline__ cplx warp_sum(cplx v) {
 }
 
 // ---------------------------------------------------------------------------------
+// FP64 tensor-core tile: D(8x8) += A(8x4) * B(4x8), mma.sync.m8n8k4.f64 (DMMA).
+// Fragment ownership (PTX ISA, .f64 m8n8k4): g = lane>>2, t = lane&3
+//   a = A[g][t],  b = B[t][g],  (c0,c1) = C[g][2t], C[g][2t+1].
+// Complex128 tiles are four real DMMAs on the (re,im) parts of the interleaved operands.
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+#ifdef DQA_EMUL
+  ::emul::dmma884(c0, c1, a, b);
+#else
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+#endif
+}
+
+struct ZTile {  // one lane's share of an 8x8 complex accumulator tile
+  double r0, r1, i0, i1;
+};
+__device__ __forceinline__ ZTile ztile_zero() {
+  ZTile z;
+  z.r0 = z.r1 = z.i0 = z.i1 = 0.0;
+  return z;
+}
+// acc += A(8 x K) * B(K x 8); a_at(row, k) and b_at(k, col) return complex values (0 outside
+// the operand), K is rounded up to a multiple of 4 by the caller's accessors returning 0.
+template <class FA, class FB>
+__device__ __forceinline__ void warp_zgemm_8x8(ZTile& acc, int K, FA a_at, FB b_at) {
+  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  for (int k0 = 0; k0 < K; k0 += 4) {
+    const cplx a = a_at(g, k0 + t);
+    const cplx b = b_at(k0 + t, g);
+    dmma884(acc.r0, acc.r1, a.x, b.x);
+    dmma884(acc.r0, acc.r1, -a.y, b.y);
+    dmma884(acc.i0, acc.i1, a.x, b.y);
+    dmma884(acc.i0, acc.i1, a.y, b.x);
+  }
+}
+
+// ---------------------------------------------------------------------------------
 // device-side view of one plan (all pointers are caller-owned device memory, carved
 // out of the workspace bound with dqa_bind_workspace)
 // ---------------------------------------------------------------------------------

@@ -90,23 +90,68 @@ __global__ void k_init_plus(DqaDev d) {
 
 // ---------------------------------------------------------------------------------
 // k_sector_qr: one (site n, sector y, instance) block of the right-canonisation sweep.
-//   M[(s,j), a] = sum_c R_{n+1, y-nbit(s)}[j,c] * A_n[a,s,c]      (m x b_n, m = q0+q1)
-//   M = Q R (Householder, R diagonal made real >= 0 as qr_stabilized does, with sgn(0):=+1)
-// shared memory: M (2chi x chi, col-major) | As (2*chi*chi) | Rs (2chi x (chi+1)) | tau | beta
+//   M[(s,j), a] = sum_c R_{n+1, y-nbit(s)}[j,c] * A_n[a,s,c]      (m x b_n, m = q0+q1)  -- DMMA tiles
+//   M = Q R (Householder; R diagonal made real >= 0 as qr_stabilized does, with sgn(0):=+1)
+// Mapping: one 8-lane group per column; the group keeps its column in registers for the whole
+// factorisation (rows li, li+8, ...), reflector k is published to shared memory by the group
+// that owns column k as soon as it has applied reflector k-1 (one __syncthreads per column),
+// dot products are 3-stage __shfl_xor reductions.  Q = H_0...H_{q-1} I is then formed column by
+// column with no block barrier at all (column j only needs reflectors j..0).
+// shared memory: M (2chi x chi, col-major; column k ends up holding reflector v_k) | tau | beta
 // ---------------------------------------------------------------------------------
 __host__ __device__ inline size_t sector_qr_smem(int chi) {
-  return sizeof(cplx) * ((size_t)2 * chi * chi + 2 * chi * chi + 2 * chi * (chi + 1) + chi) + sizeof(double) * chi;
+  return sizeof(cplx) * ((size_t)2 * chi * chi + chi) + sizeof(double) * chi;
 }
 
-__global__ void k_sector_qr(DqaDev d, int n, int mu) {
+template <int MAXS>
+__device__ __forceinline__ void sqr_publish(cplx (&col)[MAXS], int k, int m, int j, int li, cplx* Mk, cplx* tau, double* betas) {
+  // executed by every lane of the warp that contains group k; only group k == j stores
+  double ss = 0.0;
+  cplx alpha = cmk(0.0, 0.0);
+#pragma unroll
+  for (int t = 0; t < MAXS; ++t) {
+    const int row = li + 8 * t;
+    if (row > k && row < m) ss += cabs2(col[t]);
+    if (row == k) alpha = col[t];
+  }
+  ss += __shfl_xor_sync(DQA_FULL, ss, 4);
+  ss += __shfl_xor_sync(DQA_FULL, ss, 2);
+  ss += __shfl_xor_sync(DQA_FULL, ss, 1);
+  // alpha lives in lane (k & 7) of the group: sum-broadcast (all other lanes hold 0)
+  alpha.x += __shfl_xor_sync(DQA_FULL, alpha.x, 4);
+  alpha.y += __shfl_xor_sync(DQA_FULL, alpha.y, 4);
+  alpha.x += __shfl_xor_sync(DQA_FULL, alpha.x, 2);
+  alpha.y += __shfl_xor_sync(DQA_FULL, alpha.y, 2);
+  alpha.x += __shfl_xor_sync(DQA_FULL, alpha.x, 1);
+  alpha.y += __shfl_xor_sync(DQA_FULL, alpha.y, 1);
+  if (j != k) return;
+  double beta;
+  cplx t_, scal;
+  householder_gen(alpha, ss, beta, t_, scal);
+#pragma unroll
+  for (int t = 0; t < MAXS; ++t) {
+    const int row = li + 8 * t;
+    if (row > k && row < m) {
+      col[t] = cmul(col[t], scal);
+      Mk[row] = col[t];
+    }
+    if (row == k) col[t] = cmk(beta, 0.0);
+  }
+  if (li == 0) {
+    tau[k] = t_;
+    betas[k] = beta;
+  }
+}
+
+template <int MAXS>
+__global__ void __launch_bounds__(512) k_sector_qr(DqaDev d, int n, int mu) {
   DQA_DYN_SMEM(smraw);
   const int y = blockIdx.x, inst = blockIdx.y;
   const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarp = nt >> 5;
-  const int chi = d.chi, ldm = 2 * chi, ldr = chi + 1;
+  const int j = tid >> 3, li = tid & 7;  // column owned by this 8-lane group, lane in group
+  const int chi = d.chi, ldm = 2 * chi;
   cplx* M = (cplx*)smraw;
-  cplx* As = M + (size_t)ldm * chi;
-  cplx* Rs = As + (size_t)2 * chi * chi;
-  cplx* tau = Rs + (size_t)2 * chi * ldr;
+  cplx* tau = M + (size_t)ldm * chi;
   double* betas = (double*)(tau + chi);
 
   const int* bond = d.bond + inst * (d.N + 1);
@@ -124,102 +169,139 @@ __global__ void k_sector_qr(DqaDev d, int n, int mu) {
   cplx* rout = d.rbuf + (((size_t)inst * 2 + (n & 1)) * d.smax + y) * rsz;
   const cplx* a_site = d.mps + ((size_t)inst * d.N + n) * (2 * rsz);
 
-  // stage A_n (both s) and the two R blocks
-  for (int i = tid; i < bl * 2 * br; i += nt) {
-    const int c = i % br, as = i / br;
-    As[as * br + c] = a_site[as * chi + c];
-  }
-  for (int i = tid; i < m * br; i += nt) {
-    const int c = i % br, row = i / br;
-    const int s = row < q0 ? 0 : 1;
-    const int j = row - (s ? q0 : 0);
-    const int yp = s ? yp1 : yp0;
-    Rs[row * ldr + c] = rin[(size_t)yp * rsz + j * chi + c];
-  }
-  __syncthreads();
-  for (int i = tid; i < m * bl; i += nt) {
-    const int row = i % m, a = i / m;
-    const int s = row < q0 ? 0 : 1;
-    const cplx* rr = Rs + row * ldr;
-    const cplx* aa = As + (a * 2 + s) * br;
-    cplx acc = cmk(0.0, 0.0);
-    for (int c = 0; c < br; ++c) acc = cfma(rr[c], aa[c], acc);
-    M[row + a * ldm] = acc;
+  // ---- M = [R_{yp0} A_0^T ; R_{yp1} A_1^T] with FP64 tensor-core tiles ----
+  {
+    const int g = lane >> 2, t = lane & 3;
+    const int tr0 = (q0 + 7) >> 3, tr1 = (q1 + 7) >> 3, tc = (bl + 7) >> 3;
+    for (int tile = warp; tile < (tr0 + tr1) * tc; tile += nwarp) {
+      const int rt = tile / tc, a0 = (tile % tc) * 8;
+      const int s = rt < tr0 ? 0 : 1;
+      const int r0 = (s ? rt - tr0 : rt) * 8, qs = s ? q1 : q0, rowoff = s ? q0 : 0;
+      const cplx* R = rin + (size_t)(s ? yp1 : yp0) * rsz;
+      ZTile acc = ztile_zero();
+      warp_zgemm_8x8(
+          acc, br,
+          [&](int row, int kk) { return (r0 + row < qs && kk < br) ? R[(r0 + row) * chi + kk] : cmk(0.0, 0.0); },
+          [&](int kk, int col) { return (kk < br && a0 + col < bl) ? a_site[((a0 + col) * 2 + s) * chi + kk] : cmk(0.0, 0.0); });
+      const int row = r0 + g, a = a0 + 2 * t;
+      if (row < qs) {
+        if (a < bl) M[rowoff + row + a * ldm] = cmk(acc.r0, acc.i0);
+        if (a + 1 < bl) M[rowoff + row + (a + 1) * ldm] = cmk(acc.r1, acc.i1);
+      }
+    }
   }
   __syncthreads();
 
-  // Householder QR, column by column (zgeqr2)
+  // ---- Householder QR with register-resident columns ----
+  const bool has = j < bl;
+  cplx col[MAXS];
+#pragma unroll
+  for (int t = 0; t < MAXS; ++t) {
+    const int row = li + 8 * t;
+    col[t] = (has && row < m) ? M[row + j * ldm] : cmk(0.0, 0.0);
+  }
+  __syncthreads();  // M is reused for the reflectors from here on
+  if (warp == 0 && q > 0) sqr_publish<MAXS>(col, 0, m, j, li, M, tau, betas);
+  __syncthreads();
   for (int k = 0; k < q; ++k) {
-    if (warp == 0) {
-      double ss = 0.0;
-      for (int i = k + 1 + lane; i < m; i += 32) ss += cabs2(M[i + k * ldm]);
-      ss = warp_sum(ss);
-      const cplx alpha = M[k + k * ldm];
-      double beta;
-      cplx t, scal;
-      householder_gen(alpha, ss, beta, t, scal);
-      __syncwarp();
-      for (int i = k + 1 + lane; i < m; i += 32) M[i + k * ldm] = cmul(M[i + k * ldm], scal);
-      if (lane == 0) {
-        tau[k] = t;
-        betas[k] = beta;
-        M[k + k * ldm] = cmk(beta, 0.0);
-      }
-    }
-    __syncthreads();
     const cplx tk = cconj(tau[k]);  // H^H is applied
-    if (tk.x != 0.0 || tk.y != 0.0) {
-      for (int j = k + 1 + warp; j < bl; j += nwarp) {
-        cplx w = (lane == 0) ? M[k + j * ldm] : cmk(0.0, 0.0);
-        for (int i = k + 1 + lane; i < m; i += 32) w = cfmac(M[i + j * ldm], M[i + k * ldm], w);  // M_ij * conj(v_i)
-        w = warp_sum(w);
-        const cplx tw = cmul(tk, w);
-        if (lane == 0) M[k + j * ldm] = csub(M[k + j * ldm], tw);
-        for (int i = k + 1 + lane; i < m; i += 32) M[i + j * ldm] = cfms(tw, M[i + k * ldm], M[i + j * ldm]);
+    const bool act = has && j > k && (tk.x != 0.0 || tk.y != 0.0);
+    const cplx* vk = M + k * ldm;
+    cplx v[MAXS];
+    cplx w = cmk(0.0, 0.0);
+#pragma unroll
+    for (int t = 0; t < MAXS; ++t) {
+      const int row = li + 8 * t;
+      v[t] = cmk(0.0, 0.0);
+      if (act && row > k && row < m) {
+        v[t] = vk[row];
+        w = cfmac(col[t], v[t], w);  // col * conj(v)
+      }
+      if (act && row == k) w = cadd(w, col[t]);
+    }
+    w.x += __shfl_xor_sync(DQA_FULL, w.x, 4);
+    w.y += __shfl_xor_sync(DQA_FULL, w.y, 4);
+    w.x += __shfl_xor_sync(DQA_FULL, w.x, 2);
+    w.y += __shfl_xor_sync(DQA_FULL, w.y, 2);
+    w.x += __shfl_xor_sync(DQA_FULL, w.x, 1);
+    w.y += __shfl_xor_sync(DQA_FULL, w.y, 1);
+    if (act) {
+      const cplx tw = cmul(tk, w);
+#pragma unroll
+      for (int t = 0; t < MAXS; ++t) {
+        const int row = li + 8 * t;
+        if (row == k) col[t] = csub(col[t], tw);
+        if (row > k && row < m) col[t] = cfms(tw, v[t], col[t]);
       }
     }
+    if (k + 1 < q && warp == ((k + 1) >> 2)) sqr_publish<MAXS>(col, k + 1, m, j, li, M + (k + 1) * ldm, tau, betas);
     __syncthreads();
   }
 
-  // R out (row-major q x bl, ld chi), diagonal made non-negative
-  for (int i = tid; i < q * bl; i += nt) {
-    const int a = i % bl, j = i / bl;
-    cplx v = cmk(0.0, 0.0);
-    if (a >= j) {
-      v = M[j + a * ldm];
-      if (betas[j] < 0.0) v = cmk(-v.x, -v.y);
+  // ---- R out (row-major q x bl, ld chi), diagonal made non-negative ----
+  if (has) {
+#pragma unroll
+    for (int t = 0; t < MAXS; ++t) {
+      const int row = li + 8 * t;
+      if (row < q) {
+        cplx v = cmk(0.0, 0.0);
+        if (row <= j) {
+          v = col[t];
+          if (betas[row] < 0.0) v = cmk(-v.x, -v.y);
+        }
+        rout[row * chi + j] = v;
+      }
     }
-    rout[j * chi + a] = v;
   }
-  __syncthreads();
 
-  // form Q in place (zung2r)
-  for (int i = q - 1; i >= 0; --i) {
-    const cplx ti = tau[i];
-    if (ti.x != 0.0 || ti.y != 0.0) {
-      for (int j = i + 1 + warp; j < q; j += nwarp) {
-        cplx w = cmk(0.0, 0.0);
-        for (int r = i + 1 + lane; r < m; r += 32) w = cfmac(M[r + j * ldm], M[r + i * ldm], w);
-        w = warp_sum(w);
+  // ---- Q = H_0 ... H_{q-1} [I; 0]: column j needs reflectors j, j-1, ..., 0; no block barrier ----
+  {
+    cplx qc[MAXS];
+#pragma unroll
+    for (int t = 0; t < MAXS; ++t) qc[t] = (li + 8 * t == j && j < q) ? cmk(1.0, 0.0) : cmk(0.0, 0.0);
+    int imax = 4 * warp + 3;
+    if (imax > q - 1) imax = q - 1;
+    for (int i = imax; i >= 0; --i) {  // warp-uniform trip count
+      const cplx ti = tau[i];
+      const bool act = (j < q) && (i <= j) && (ti.x != 0.0 || ti.y != 0.0);
+      const cplx* vi = M + i * ldm;
+      cplx v[MAXS];
+      cplx w = cmk(0.0, 0.0);
+#pragma unroll
+      for (int t = 0; t < MAXS; ++t) {
+        const int row = li + 8 * t;
+        v[t] = cmk(0.0, 0.0);
+        if (act && row > i && row < m) {
+          v[t] = vi[row];
+          w = cfmac(qc[t], v[t], w);
+        }
+        if (act && row == i) w = cadd(w, qc[t]);
+      }
+      w.x += __shfl_xor_sync(DQA_FULL, w.x, 4);
+      w.y += __shfl_xor_sync(DQA_FULL, w.y, 4);
+      w.x += __shfl_xor_sync(DQA_FULL, w.x, 2);
+      w.y += __shfl_xor_sync(DQA_FULL, w.y, 2);
+      w.x += __shfl_xor_sync(DQA_FULL, w.x, 1);
+      w.y += __shfl_xor_sync(DQA_FULL, w.y, 1);
+      if (act) {
         const cplx tw = cmul(ti, w);
-        if (lane == 0) M[i + j * ldm] = cmk(-tw.x, -tw.y);
-        for (int r = i + 1 + lane; r < m; r += 32) M[r + j * ldm] = cfms(tw, M[r + i * ldm], M[r + j * ldm]);
+#pragma unroll
+        for (int t = 0; t < MAXS; ++t) {
+          const int row = li + 8 * t;
+          if (row == i) qc[t] = csub(qc[t], tw);
+          if (row > i && row < m) qc[t] = cfms(tw, v[t], qc[t]);
+        }
       }
     }
-    __syncthreads();
-    const cplx nti = cmk(-ti.x, -ti.y);
-    for (int r = i + 1 + tid; r < m; r += nt) M[r + i * ldm] = cmul(nti, M[r + i * ldm]);
-    for (int r = tid; r < i; r += nt) M[r + i * ldm] = cmk(0.0, 0.0);
-    if (tid == 0) M[i + i * ldm] = cmk(1.0 - ti.x, -ti.y);
-    __syncthreads();
-  }
-
-  cplx* qout = d.qbuf + ((size_t)inst * d.nsec_total + dqa_secbase(d.N, n) + y) * (2 * rsz);
-  for (int i = tid; i < m * q; i += nt) {
-    const int row = i % m, j = i / m;
-    cplx v = M[row + j * ldm];
-    if (betas[j] < 0.0) v = cmk(-v.x, -v.y);
-    qout[row + j * ldm] = v;
+    if (j < q) {
+      cplx* qout = d.qbuf + ((size_t)inst * d.nsec_total + dqa_secbase(d.N, n) + y) * (2 * rsz);
+      const double sg = betas[j] < 0.0 ? -1.0 : 1.0;
+#pragma unroll
+      for (int t = 0; t < MAXS; ++t) {
+        const int row = li + 8 * t;
+        if (row < m) qout[row + j * ldm] = cscale(qc[t], sg);
+      }
+    }
   }
   if (tid == 0) {
     d.qdim[((size_t)inst * (d.N + 1) + n) * d.smax + y] = q;
@@ -278,10 +360,11 @@ __global__ void k_theta0(DqaDev d, int mu, int p) {
 //   Theta_l[(beta,s), off'_{y'} + j'] = sum_j C_y[beta,j] Q_{l,y}[(rowoff_s + j'), j],  y' = y - nbit_l(s)
 // grid (N-l+1 sectors of bond l, batch); shared: C (chi x chi)
 // ---------------------------------------------------------------------------------
-__global__ void k_theta(DqaDev d, int l, int mu) {
+__global__ void __launch_bounds__(256) k_theta(DqaDev d, int l, int mu) {
   DQA_DYN_SMEM(smraw);
   cplx* C = (cplx*)smraw;
-  const int y = blockIdx.x, inst = blockIdx.y, tid = threadIdx.x, nt = blockDim.x;
+  const int y = blockIdx.x, inst = blockIdx.y, tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5, g = lane >> 2, t = lane & 3;
   const int chi = d.chi, ldq = 2 * chi, ld = d.ld_theta;
   const size_t rsz = (size_t)chi * chi;
   const int* bond = d.bond + inst * (d.N + 1);
@@ -295,26 +378,45 @@ __global__ void k_theta(DqaDev d, int l, int mu) {
   cplx* thc = d.theta + ((size_t)inst * 2 + (l & 1)) * (size_t)(2 * chi) * ld;
   const cplx* U = d.mps + ((size_t)inst * d.N + (l - 1)) * (2 * rsz);
   const double scale = d.scale[inst];
-  for (int i = tid; i < cl * qy; i += nt) {
-    const int j = i % qy, b = i / qy;
-    cplx acc = cmk(0.0, 0.0);
-    for (int r = 0; r < mrp; ++r) acc = cfmac(thp[(size_t)r * ld + offy + j], U[r * chi + b], acc);
-    C[b * qy + j] = cscale(acc, scale);
+  const int tb = (cl + 7) >> 3, tj = (qy + 7) >> 3;
+  // GEMM 1 (DMMA): C[b,j] = scale * sum_r conj(U[r,b]) Theta_{l-1}[r, offy+j]
+  for (int tile = warp; tile < tb * tj; tile += nwarp) {
+    const int b0 = (tile / tj) * 8, j0 = (tile % tj) * 8;
+    ZTile acc = ztile_zero();
+    warp_zgemm_8x8(
+        acc, mrp,
+        [&](int row, int kk) { return (b0 + row < cl && kk < mrp) ? cconj(U[kk * chi + b0 + row]) : cmk(0.0, 0.0); },
+        [&](int kk, int col) { return (kk < mrp && j0 + col < qy) ? thp[(size_t)kk * ld + offy + j0 + col] : cmk(0.0, 0.0); });
+    const int b = b0 + g, j = j0 + 2 * t;
+    if (b < cl) {
+      if (j < qy) C[b * qy + j] = cmk(acc.r0 * scale, acc.i0 * scale);
+      if (j + 1 < qy) C[b * qy + j + 1] = cmk(acc.r1 * scale, acc.i1 * scale);
+    }
   }
   __syncthreads();
-  const cplx* Q = d.qbuf + ((size_t)inst * d.nsec_total + dqa_secbase(d.N, l) + y) * (2 * rsz);
+  const cplx* Qm = d.qbuf + ((size_t)inst * d.nsec_total + dqa_secbase(d.N, l) + y) * (2 * rsz);
   const int yp0 = y - hb, yp1 = y - (hb ^ 1);
   const int v0 = (yp0 >= 0 && yp0 <= ymax_out), v1 = (yp1 >= 0 && yp1 <= ymax_out);
   const int q0 = v0 ? qd1[yp0] : 0;
+  // GEMM 2 (DMMA): Theta_l[(b,s), off' + j'] = sum_j C[b,j] Q[(rowoff_s + j'), j]
   for (int s = 0; s < 2; ++s) {
     const int yp = s ? yp1 : yp0;
     if (!(s ? v1 : v0)) continue;
     const int qo = qd1[yp], offo = qdim_prefix(qd1, yp), rowoff = s ? q0 : 0;
-    for (int i = tid; i < cl * qo; i += nt) {
-      const int jp = i % qo, b = i / qo;
-      cplx acc = cmk(0.0, 0.0);
-      for (int j = 0; j < qy; ++j) acc = cfma(C[b * qy + j], Q[(rowoff + jp) + j * ldq], acc);
-      thc[(size_t)(b * 2 + s) * ld + offo + jp] = acc;
+    const int to = (qo + 7) >> 3;
+    for (int tile = warp; tile < tb * to; tile += nwarp) {
+      const int b0 = (tile / to) * 8, p0 = (tile % to) * 8;
+      ZTile acc = ztile_zero();
+      warp_zgemm_8x8(
+          acc, qy,
+          [&](int row, int kk) { return (b0 + row < cl && kk < qy) ? C[(b0 + row) * qy + kk] : cmk(0.0, 0.0); },
+          [&](int kk, int col) { return (kk < qy && p0 + col < qo) ? Qm[(rowoff + p0 + col) + kk * ldq] : cmk(0.0, 0.0); });
+      const int b = b0 + g, jp = p0 + 2 * t;
+      if (b < cl) {
+        cplx* dst = thc + (size_t)(b * 2 + s) * ld + offo;
+        if (jp < qo) dst[jp] = cmk(acc.r0, acc.i0);
+        if (jp + 1 < qo) dst[jp + 1] = cmk(acc.r1, acc.i1);
+      }
     }
     if (tid == 0) atomicAdd(&d.counters[inst * DQA_NCNT + 7], 8ull * cl * qo * qy);
   }
@@ -735,15 +837,16 @@ __global__ void k_mixer(DqaDev d, double cb, double sb) {
 // ---------------------------------------------------------------------------------
 __host__ __device__ inline size_t energy_smem(int chi) { return sizeof(cplx) * (size_t)4 * chi * chi; }
 
-__global__ void k_energy(DqaDev d) {
+__global__ void __launch_bounds__(256) k_energy(DqaDev d) {
   DQA_DYN_SMEM(smraw);
-  const int k = blockIdx.x, mu = blockIdx.y, inst = blockIdx.z, tid = threadIdx.x, nt = blockDim.x;
+  const int k = blockIdx.x, mu = blockIdx.y, inst = blockIdx.z, tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5, g = lane >> 2, t = lane & 3;
   const int chi = d.chi;
   const size_t rsz = (size_t)chi * chi;
   cplx* E = (cplx*)smraw;
   cplx* E2 = E + rsz;
-  cplx* W = E2 + rsz;
-  cplx* As = W + rsz;
+  cplx* W0 = E2 + rsz;
+  cplx* W1 = W0 + rsz;
   const int* bond = d.bond + inst * (d.N + 1);
   const uint8_t* hb = d.hbit + ((size_t)inst * d.n_xi + mu) * d.N;
   const cplx wk = d.phase[k];  // exp(i pi q / D) with q = k*e, e = 2
@@ -752,31 +855,45 @@ __global__ void k_energy(DqaDev d) {
   for (int i = 0; i < d.N; ++i) {
     const int bl = bond[i], br = bond[i + 1];
     const cplx* a = d.mps + ((size_t)inst * d.N + i) * (2 * rsz);
-    for (int s = 0; s < 2; ++s) {
-      for (int t = tid; t < bl * br; t += nt) {
-        const int b = t % br, r = t / br;
-        As[r * br + b] = a[(r * 2 + s) * chi + b];
+    const int tr = (bl + 7) >> 3, tc = (br + 7) >> 3;
+    // phase 1 (DMMA): W_s[c,b] = sum_a E[a,c] A[a,s,b], both s
+    for (int tile = warp; tile < 2 * tr * tc; tile += nwarp) {
+      const int s = tile / (tr * tc), rem = tile % (tr * tc), c0 = (rem / tc) * 8, b0 = (rem % tc) * 8;
+      ZTile acc = ztile_zero();
+      warp_zgemm_8x8(
+          acc, bl,
+          [&](int row, int kk) { return (c0 + row < bl && kk < bl) ? E[kk * bl + c0 + row] : cmk(0.0, 0.0); },
+          [&](int kk, int col) { return (kk < bl && b0 + col < br) ? a[(kk * 2 + s) * chi + b0 + col] : cmk(0.0, 0.0); });
+      cplx* W = s ? W1 : W0;
+      const int c = c0 + g, b = b0 + 2 * t;
+      if (c < bl) {
+        if (b < br) W[c * br + b] = cmk(acc.r0, acc.i0);
+        if (b + 1 < br) W[c * br + b + 1] = cmk(acc.r1, acc.i1);
       }
-      __syncthreads();
-      // W[c,b] = sum_a E[a,c] A_s[a,b]
-      for (int t = tid; t < bl * br; t += nt) {
-        const int b = t % br, c = t / br;
-        cplx acc = cmk(0.0, 0.0);
-        for (int aa = 0; aa < bl; ++aa) acc = cfma(E[aa * bl + c], As[aa * br + b], acc);
-        W[c * br + b] = acc;
-      }
-      __syncthreads();
-      const cplx ph = (hb[i] ^ s) ? wk : cmk(1.0, 0.0);
-      // E2[b,dd] (+)= ph * sum_c W[c,b] conj(A_s[c,dd])
-      for (int t = tid; t < br * br; t += nt) {
-        const int dd = t % br, b = t / br;
-        cplx acc = cmk(0.0, 0.0);
-        for (int c = 0; c < bl; ++c) acc = cfmac(W[c * br + b], As[c * br + dd], acc);
-        acc = cmul(ph, acc);
-        E2[b * br + dd] = s ? cadd(E2[b * br + dd], acc) : acc;
-      }
-      __syncthreads();
     }
+    __syncthreads();
+    // phase 2 (DMMA): E2[b,dd] = sum_s ph_s sum_c W_s[c,b] conj(A[c,s,dd])
+    for (int tile = warp; tile < tc * tc; tile += nwarp) {
+      const int b0 = (tile / tc) * 8, d0 = (tile % tc) * 8;
+      cplx out0 = cmk(0.0, 0.0), out1 = cmk(0.0, 0.0);
+      for (int s = 0; s < 2; ++s) {
+        const cplx* W = s ? W1 : W0;
+        ZTile acc = ztile_zero();
+        warp_zgemm_8x8(
+            acc, bl,
+            [&](int row, int kk) { return (b0 + row < br && kk < bl) ? W[kk * br + b0 + row] : cmk(0.0, 0.0); },
+            [&](int kk, int col) { return (kk < bl && d0 + col < br) ? cconj(a[(kk * 2 + s) * chi + d0 + col]) : cmk(0.0, 0.0); });
+        const cplx ph = (hb[i] ^ s) ? wk : cmk(1.0, 0.0);
+        out0 = cfma(ph, cmk(acc.r0, acc.i0), out0);
+        out1 = cfma(ph, cmk(acc.r1, acc.i1), out1);
+      }
+      const int b = b0 + g, dd = d0 + 2 * t;
+      if (b < br) {
+        if (dd < br) E2[b * br + dd] = out0;
+        if (dd + 1 < br) E2[b * br + dd + 1] = out1;
+      }
+    }
+    __syncthreads();
     cplx* t2 = E;
     E = E2;
     E2 = t2;

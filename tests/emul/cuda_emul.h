@@ -141,6 +141,27 @@ inline T shfl_generic(T v, int src_lane) {
   return out;
 }
 
+// mma.sync.m8n8k4.f64 with the PTX fragment layout (a=A[g][t], b=B[t][g], c=C[g][2t..2t+1])
+inline void dmma884(double& c0, double& c1, double a, double b) {
+  State& s = st();
+  int t0 = s.cur, w = warp_of(t0), lane = t0 % 32;
+  double2 mine;
+  mine.x = a;
+  mine.y = b;
+  s.w_buf[w * 32 + lane] = mine;
+  syncwarp();
+  const int g = lane >> 2, t = lane & 3;
+  double s0 = 0.0, s1 = 0.0;
+  for (int k = 0; k < 4; ++k) {
+    const double av = s.w_buf[w * 32 + g * 4 + k].x;             // A[g][k]
+    s0 += av * s.w_buf[w * 32 + (2 * t) * 4 + k].y;              // B[k][2t]
+    s1 += av * s.w_buf[w * 32 + (2 * t + 1) * 4 + k].y;          // B[k][2t+1]
+  }
+  syncwarp();
+  c0 += s0;
+  c1 += s1;
+}
+
 inline void fiber_entry() {
   State& s = st();
   int me = s.cur;

@@ -42,7 +42,7 @@ def parse():
     ap.add_argument("--chi", type=int, default=32)
     ap.add_argument("--P", type=int, default=1000)
     ap.add_argument("--dt", type=float, default=1.0)
-    ap.add_argument("--batch", type=int, default=148, help="realisations per GPU")
+    ap.add_argument("--batch", type=int, default=888, help="realisations per GPU (888 = 148 SMs x 6: whole waves at 2 and 3 CTAs/SM)")
     ap.add_argument("--cpu-seconds", type=float, default=200.0, help="budget of the CPU legs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")

@@ -26,6 +26,7 @@ struct dqa_handle {
   bool have_patterns, have_fourier, have_state;
   int t_qr, t_theta, t_svd, t_energy;  // block sizes
   int t_lq;
+  bool jac_nocache, jac_cache32;
   char err[512];
   // profiling
   bool profiling;
@@ -115,7 +116,7 @@ extern "C" int dqa_create(dqa_t** out, const dqa_config* cfg) {
   if (c.N < 2 || c.n_xi < 1 || c.P < 1 || c.chi < 1 || c.batch < 1) return fail(h, DQA_EINVAL, "N>=2, n_xi>=1, P>=1, chi>=1, batch>=1 required");
   if (c.N > 254) return fail(h, DQA_ELIMIT, "N=%d > 254 not supported", c.N);
   if (sector_qr_smem(c.chi) > 227 * 1024 || svd_smem(c.chi) > 227 * 1024 || energy_smem(c.chi) > 227 * 1024 ||
-      lq_smem(((c.chi * (c.N + 1)) + 1) & ~1) > 227 * 1024)
+      lq_smem(c.chi * (c.N + 1), c.chi) > 227 * 1024)
     return fail(h, DQA_ELIMIT, "chi=%d needs more than 227 KB of shared memory per CTA in this build (max chi 48)", c.chi);
   h->stream = (cudaStream_t)c.stream;
   h->ws = nullptr;
@@ -136,6 +137,18 @@ extern "C" int dqa_create(dqa_t** out, const dqa_config* cfg) {
   d.smax = c.N + 1;
   d.ld_theta = ((c.chi * (c.N + 1)) + 1) & ~1;
   d.nsec_total = dqa_secbase(c.N, c.N);
+  {
+    // bond n (1..N-1) of the input MPS is at most min(chi, 2^n, 2^(N-n)); it carries N-n+1 sectors
+    long qm = 1;
+    for (int n = 1; n < c.N; ++n) {
+      long b = c.chi;
+      if (n < 30 && (1L << n) < b) b = 1L << n;
+      if (c.N - n < 30 && (1L << (c.N - n)) < b) b = 1L << (c.N - n);
+      const long v = b * (c.N - n + 1);
+      if (v > qm) qm = v;
+    }
+    d.qmax = (int)qm;
+  }
   d.kh = d.D / 2 + 1;
   d.max_sweeps = c.max_sweeps;
   d.cutoff = c.cutoff;
@@ -143,22 +156,26 @@ extern "C" int dqa_create(dqa_t** out, const dqa_config* cfg) {
 #ifdef DQA_EMUL
   h->t_qr = 32 * ((8 * c.chi + 31) / 32); h->t_theta = 64; h->t_svd = 64; h->t_energy = 64; h->t_lq = 64;
   if (h->t_qr < 64) h->t_qr = 64;
+  h->jac_nocache = false; h->jac_cache32 = true;
 #else
   h->t_qr = 32 * ((8 * c.chi + 31) / 32);  // one 8-lane group per column of the sector block
   if (h->t_qr < 64) h->t_qr = 64;
   h->t_theta = 256;
   {
     // Jacobi: few warps per CTA, each owning ~8 column pairs per round; several CTAs share an SM
-    int warps = (c.chi + 7) / 8;
+    int warps = (c.chi + 3) / 4;  // 4 column pairs per warp and round: one pass per round
     if (warps < 2) warps = 2;
-    if (warps > 8) warps = 8;
+    if (warps > 16) warps = 16;
     const char* env = getenv("DQA_JAC_WARPS");
-    if (env && atoi(env) >= 1 && atoi(env) <= 8) warps = atoi(env);
+    if (env && atoi(env) >= 1 && atoi(env) <= 16) warps = atoi(env);
     if (warps < (c.chi + 31) / 32) warps = (c.chi + 31) / 32;  // at most 32 column pairs per warp
     h->t_svd = 32 * warps;
+    env = getenv("DQA_JAC_CACHE");  // 0: never keep the pair in registers; 2: also for chi in (16,32] (costs occupancy)
+    h->jac_nocache = env && atoi(env) == 0;
+    h->jac_cache32 = env && atoi(env) == 2;
     h->t_lq = c.chi <= 8 ? 128 : (c.chi <= 16 ? 256 : 512);
     env = getenv("DQA_LQ_THREADS");
-    if (env && atoi(env) >= 32 && atoi(env) <= 1024) h->t_lq = atoi(env) & ~31;
+    if (env && atoi(env) >= 32 && atoi(env) <= 32 * LQ_MAXW) h->t_lq = atoi(env) & ~31;
   }
   h->t_energy = c.chi <= 8 ? 64 : 256;
 #endif
@@ -167,8 +184,10 @@ extern "C" int dqa_create(dqa_t** out, const dqa_config* cfg) {
   CK(cudaFuncSetAttribute(k_sector_qr<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sector_qr_smem(c.chi)));
   CK(cudaFuncSetAttribute(k_sector_qr<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sector_qr_smem(c.chi)));
   CK(cudaFuncSetAttribute(k_sector_qr<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sector_qr_smem(c.chi)));
-  CK(cudaFuncSetAttribute(k_jacobi, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)svd_smem(c.chi)));
-  CK(cudaFuncSetAttribute(k_lq, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lq_smem(h->dev.ld_theta)));
+  CK(cudaFuncSetAttribute(k_jacobi<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)svd_smem(c.chi)));
+  CK(cudaFuncSetAttribute(k_jacobi<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)svd_smem(c.chi)));
+  CK(cudaFuncSetAttribute(k_jacobi<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)svd_smem(c.chi)));
+  CK(cudaFuncSetAttribute(k_lq, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lq_smem(h->dev.qmax, c.chi)));
   CK(cudaFuncSetAttribute(k_energy, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)energy_smem(c.chi)));
   CK(cudaFuncSetAttribute(k_theta, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(cplx) * c.chi * c.chi)));
   return DQA_OK;
@@ -354,10 +373,16 @@ static int launch_truncate(dqa_t* h, int p, int mu) {
       prof_b(h);
     }
     prof_a(h, 2);
-    HL(k_lq, dim3(d.batch), dim3(h->t_lq), lq_smem(d.ld_theta), h->stream, d, l);
+    HL(k_lq, dim3(d.batch), dim3(h->t_lq), lq_smem(d.qmax, d.chi), h->stream, d, l);
     prof_b(h);
     prof_a(h, 5);
-    HL(k_jacobi, dim3(d.batch), dim3(h->t_svd), svd_smem(d.chi), h->stream, d, l, mu, p);
+    {
+      // register-cached variant needs one pass per round (4 pairs per warp) and 2chi <= 8*RS rows
+      const bool one_pass = (h->t_svd / 32) * 4 >= d.chi;
+      if (one_pass && d.chi <= 16 && !h->jac_nocache) HL(k_jacobi<4>, dim3(d.batch), dim3(h->t_svd), svd_smem(d.chi), h->stream, d, l, mu, p);
+      else if (one_pass && d.chi <= 32 && h->jac_cache32) HL(k_jacobi<8>, dim3(d.batch), dim3(h->t_svd), svd_smem(d.chi), h->stream, d, l, mu, p);
+      else HL(k_jacobi<0>, dim3(d.batch), dim3(h->t_svd), svd_smem(d.chi), h->stream, d, l, mu, p);
+    }
     prof_b(h);
   }
   CK(cudaGetLastError());
@@ -515,6 +540,17 @@ extern "C" int dqa_set_mps(dqa_t* h, int inst, int site, const double* buf, int 
   if (!buf || inst < 0 || inst >= h->cfg.batch || site < 0 || site >= N) return DQA_EINVAL;
   if (l < 1 || r < 1 || l > chi || r > chi) return fail(h, DQA_ELIMIT, "site %d bonds (%d,%d) exceed chi=%d", site, l, r, chi);
   if ((site == 0 && l != 1) || (site == N - 1 && r != 1)) return fail(h, DQA_EINVAL, "boundary bonds must be 1");
+  {
+    // the sector kernels size their shared memory for bonds <= min(chi, 2^n, 2^(N-n)) (anything larger is
+    // rank-deficient padding; compress such a state first)
+    const int bn[2] = {site, site + 1}, bv[2] = {l, r};
+    for (int e = 0; e < 2; ++e) {
+      long cap = chi;
+      if (bn[e] < 30 && (1L << bn[e]) < cap) cap = 1L << bn[e];
+      if (N - bn[e] < 30 && (1L << (N - bn[e])) < cap) cap = 1L << (N - bn[e]);
+      if (bv[e] > cap) return fail(h, DQA_ELIMIT, "bond %d has dimension %d > min(chi, 2^n, 2^(N-n)) = %ld", bn[e], bv[e], cap);
+    }
+  }
   std::vector<std::complex<double>> pad((size_t)2 * chi * chi, std::complex<double>(0.0, 0.0));
   const std::complex<double>* in = reinterpret_cast<const std::complex<double>*>(buf);
   for (int a = 0; a < l; ++a)

@@ -107,6 +107,7 @@ __device__ __forceinline__ ZTile ztile_zero() {
 template <class FA, class FB>
 __device__ __forceinline__ void warp_zgemm_8x8(ZTile& acc, int K, FA a_at, FB b_at) {
   const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+#pragma unroll 4
   for (int k0 = 0; k0 < K; k0 += 4) {
     const cplx a = a_at(g, k0 + t);
     const cplx b = b_at(k0 + t, g);
@@ -125,6 +126,7 @@ struct DqaDev {
   int N, D, n_xi, chi, batch, P;
   int smax;        // N+1 sectors at most per bond
   int ld_theta;    // row stride of Theta (>= chi*(N+1))
+  int qmax;        // bound on the live columns of Theta: max_n min(chi,2^n,2^(N-n)) * (N-n+1)
   int nsec_total;  // number of (site, sector) Q blocks per instance
   int kh;          // D/2+1: independent Fourier modes of the energy sweep
   int max_sweeps;
@@ -162,4 +164,5 @@ enum {
   DQA_ST_NONFINITE = 1,
   DQA_ST_ZERONORM = 2,
   DQA_ST_NOCONV = 4,
+  DQA_ST_LIMIT = 8,
 };

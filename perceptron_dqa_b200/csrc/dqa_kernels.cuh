@@ -103,13 +103,15 @@ __host__ __device__ inline size_t sector_qr_smem(int chi) {
   return sizeof(cplx) * ((size_t)2 * chi * chi + chi) + sizeof(double) * chi;
 }
 
-template <int MAXS>
+// All three per-column routines are specialised on T0 = k>>3, the first register slot that still
+// holds live rows (rows <= k are finished), so finished slots cost no instructions.
+template <int MAXS, int T0>
 __device__ __forceinline__ void sqr_publish(cplx (&col)[MAXS], int k, int m, int j, int li, cplx* Mk, cplx* tau, double* betas) {
   // executed by every lane of the warp that contains group k; only group k == j stores
   double ss = 0.0;
   cplx alpha = cmk(0.0, 0.0);
 #pragma unroll
-  for (int t = 0; t < MAXS; ++t) {
+  for (int t = T0; t < MAXS; ++t) {
     const int row = li + 8 * t;
     if (row > k && row < m) ss += cabs2(col[t]);
     if (row == k) alpha = col[t];
@@ -129,7 +131,7 @@ __device__ __forceinline__ void sqr_publish(cplx (&col)[MAXS], int k, int m, int
   cplx t_, scal;
   householder_gen(alpha, ss, beta, t_, scal);
 #pragma unroll
-  for (int t = 0; t < MAXS; ++t) {
+  for (int t = T0; t < MAXS; ++t) {
     const int row = li + 8 * t;
     if (row > k && row < m) {
       col[t] = cmul(col[t], scal);
@@ -142,6 +144,50 @@ __device__ __forceinline__ void sqr_publish(cplx (&col)[MAXS], int k, int m, int
     betas[k] = beta;
   }
 }
+
+// col <- (I - tk v v^H) col for the group's column, v = reflector k (rows > k in shared memory, v_k = 1)
+template <int MAXS, int T0>
+__device__ __forceinline__ void sqr_apply(cplx (&col)[MAXS], const cplx* vk, cplx tk, int k, int m, int li, bool act) {
+  cplx v[MAXS];
+  cplx w = cmk(0.0, 0.0);
+#pragma unroll
+  for (int t = T0; t < MAXS; ++t) {
+    const int row = li + 8 * t;
+    v[t] = cmk(0.0, 0.0);
+    if (act && row > k && row < m) {
+      v[t] = vk[row];
+      w = cfmac(col[t], v[t], w);  // col * conj(v)
+    }
+    if (act && row == k) w = cadd(w, col[t]);
+  }
+  w.x += __shfl_xor_sync(DQA_FULL, w.x, 4);
+  w.y += __shfl_xor_sync(DQA_FULL, w.y, 4);
+  w.x += __shfl_xor_sync(DQA_FULL, w.x, 2);
+  w.y += __shfl_xor_sync(DQA_FULL, w.y, 2);
+  w.x += __shfl_xor_sync(DQA_FULL, w.x, 1);
+  w.y += __shfl_xor_sync(DQA_FULL, w.y, 1);
+  if (act) {
+    const cplx tw = cmul(tk, w);
+#pragma unroll
+    for (int t = T0; t < MAXS; ++t) {
+      const int row = li + 8 * t;
+      if (row == k) col[t] = csub(col[t], tw);
+      if (row > k && row < m) col[t] = cfms(tw, v[t], col[t]);
+    }
+  }
+}
+
+// dispatch on the first live slot rounded down to a multiple of 4 (3 code variants at most: the
+// fully specialised 12-way switch overflowed the instruction cache and ran slower)
+#define SQR_CASE(T0, CALL) \
+  case T0:                 \
+    if (T0 < MAXS) { CALL(T0 < MAXS ? T0 : 0); } \
+    break;
+#define SQR_DISPATCH(slot, CALL)                               \
+  switch ((slot) & ~3) {                                        \
+    SQR_CASE(0, CALL) SQR_CASE(4, CALL) SQR_CASE(8, CALL)       \
+    default: break;                                             \
+  }
 
 template <int MAXS>
 __global__ void __launch_bounds__(512) k_sector_qr(DqaDev d, int n, int mu) {
@@ -201,40 +247,19 @@ __global__ void __launch_bounds__(512) k_sector_qr(DqaDev d, int n, int mu) {
     col[t] = (has && row < m) ? M[row + j * ldm] : cmk(0.0, 0.0);
   }
   __syncthreads();  // M is reused for the reflectors from here on
-  if (warp == 0 && q > 0) sqr_publish<MAXS>(col, 0, m, j, li, M, tau, betas);
+  if (warp == 0 && q > 0) sqr_publish<MAXS, 0>(col, 0, m, j, li, M, tau, betas);
   __syncthreads();
   for (int k = 0; k < q; ++k) {
     const cplx tk = cconj(tau[k]);  // H^H is applied
     const bool act = has && j > k && (tk.x != 0.0 || tk.y != 0.0);
     const cplx* vk = M + k * ldm;
-    cplx v[MAXS];
-    cplx w = cmk(0.0, 0.0);
-#pragma unroll
-    for (int t = 0; t < MAXS; ++t) {
-      const int row = li + 8 * t;
-      v[t] = cmk(0.0, 0.0);
-      if (act && row > k && row < m) {
-        v[t] = vk[row];
-        w = cfmac(col[t], v[t], w);  // col * conj(v)
-      }
-      if (act && row == k) w = cadd(w, col[t]);
+#define SQR_CALL_APPLY(T0) sqr_apply<MAXS, T0>(col, vk, tk, k, m, li, act)
+    SQR_DISPATCH(k >> 3, SQR_CALL_APPLY)
+    if (k + 1 < q && warp == ((k + 1) >> 2)) {
+      const int k1 = k + 1;
+#define SQR_CALL_PUB(T0) sqr_publish<MAXS, T0>(col, k1, m, j, li, M + k1 * ldm, tau, betas)
+      SQR_DISPATCH(k1 >> 3, SQR_CALL_PUB)
     }
-    w.x += __shfl_xor_sync(DQA_FULL, w.x, 4);
-    w.y += __shfl_xor_sync(DQA_FULL, w.y, 4);
-    w.x += __shfl_xor_sync(DQA_FULL, w.x, 2);
-    w.y += __shfl_xor_sync(DQA_FULL, w.y, 2);
-    w.x += __shfl_xor_sync(DQA_FULL, w.x, 1);
-    w.y += __shfl_xor_sync(DQA_FULL, w.y, 1);
-    if (act) {
-      const cplx tw = cmul(tk, w);
-#pragma unroll
-      for (int t = 0; t < MAXS; ++t) {
-        const int row = li + 8 * t;
-        if (row == k) col[t] = csub(col[t], tw);
-        if (row > k && row < m) col[t] = cfms(tw, v[t], col[t]);
-      }
-    }
-    if (k + 1 < q && warp == ((k + 1) >> 2)) sqr_publish<MAXS>(col, k + 1, m, j, li, M + (k + 1) * ldm, tau, betas);
     __syncthreads();
   }
 
@@ -265,33 +290,8 @@ __global__ void __launch_bounds__(512) k_sector_qr(DqaDev d, int n, int mu) {
       const cplx ti = tau[i];
       const bool act = (j < q) && (i <= j) && (ti.x != 0.0 || ti.y != 0.0);
       const cplx* vi = M + i * ldm;
-      cplx v[MAXS];
-      cplx w = cmk(0.0, 0.0);
-#pragma unroll
-      for (int t = 0; t < MAXS; ++t) {
-        const int row = li + 8 * t;
-        v[t] = cmk(0.0, 0.0);
-        if (act && row > i && row < m) {
-          v[t] = vi[row];
-          w = cfmac(qc[t], v[t], w);
-        }
-        if (act && row == i) w = cadd(w, qc[t]);
-      }
-      w.x += __shfl_xor_sync(DQA_FULL, w.x, 4);
-      w.y += __shfl_xor_sync(DQA_FULL, w.y, 4);
-      w.x += __shfl_xor_sync(DQA_FULL, w.x, 2);
-      w.y += __shfl_xor_sync(DQA_FULL, w.y, 2);
-      w.x += __shfl_xor_sync(DQA_FULL, w.x, 1);
-      w.y += __shfl_xor_sync(DQA_FULL, w.y, 1);
-      if (act) {
-        const cplx tw = cmul(ti, w);
-#pragma unroll
-        for (int t = 0; t < MAXS; ++t) {
-          const int row = li + 8 * t;
-          if (row == i) qc[t] = csub(qc[t], tw);
-          if (row > i && row < m) qc[t] = cfms(tw, v[t], qc[t]);
-        }
-      }
+#define SQR_CALL_Q(T0) sqr_apply<MAXS, T0>(qc, vi, ti, i, m, li, act)
+      SQR_DISPATCH(i >> 3, SQR_CALL_Q)
     }
     if (j < q) {
       cplx* qout = d.qbuf + ((size_t)inst * d.nsec_total + dqa_secbase(d.N, n) + y) * (2 * rsz);
@@ -432,24 +432,32 @@ __global__ void __launch_bounds__(256) k_theta(DqaDev d, int l, int mu) {
 // shared: Vp (PB x npad) | Tm (PB x PB) | Sg (PB x PB) | taus (PB)
 // ---------------------------------------------------------------------------------
 #define LQ_PB 8
+#define LQ_MAXW 16  // partial-W tiles kept in shared memory (>= row tiles, <= warps per CTA)
 __host__ __device__ inline int lq_npad(int ncols) { return ((ncols + 7) & ~7) + 4; }
-__host__ __device__ inline size_t lq_smem(int ld_theta) {
-  return sizeof(cplx) * ((size_t)LQ_PB * lq_npad(ld_theta) + 2 * LQ_PB * LQ_PB + LQ_PB);
+// qmax = largest number of Theta columns any cut can have (host-computed bound), chi sets the row tiles
+__host__ __device__ inline size_t lq_smem(int qmax, int chi) {
+  return sizeof(cplx) * ((size_t)LQ_PB * lq_npad(qmax) + 2 * LQ_PB * LQ_PB + LQ_PB + (size_t)LQ_MAXW * 64 + (size_t)((2 * chi + 7) / 8) * 64);
 }
 
 __global__ void __launch_bounds__(1024) k_lq(DqaDev d, int l) {
   DQA_DYN_SMEM(smraw);
   const int inst = blockIdx.x, tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarp = nt >> 5;
-  const int chi = d.chi, ld = d.ld_theta, npad = lq_npad(ld);
+  const int chi = d.chi, ld = d.ld_theta, npad = lq_npad(d.qmax);
   cplx* Vp = (cplx*)smraw;
   cplx* Tm = Vp + (size_t)LQ_PB * npad;
   cplx* Sg = Tm + LQ_PB * LQ_PB;
   cplx* taus = Sg + LQ_PB * LQ_PB;
+  cplx* Wp = taus + LQ_PB;            // LQ_MAXW partial 8x8 tiles
+  cplx* Zs = Wp + (size_t)LQ_MAXW * 64;  // up to 16 row tiles (2chi <= 128 rows)
   const int* bond = d.bond + inst * (d.N + 1);
   const int mr = 2 * bond[l];
   const int* qd1 = d.qdim + ((size_t)inst * (d.N + 1) + (l + 1)) * d.smax;
   const int Q = qdim_prefix(qd1, d.N - l);
   const int k = mr < Q ? mr : Q;
+  if (Q > d.qmax) {  // cannot happen for states accepted by dqa_set_mps; never overrun shared memory
+    if (tid == 0) atomicOr(&d.status[inst], DQA_ST_LIMIT);
+    return;
+  }
   const cplx* th = d.theta + ((size_t)inst * 2 + (l & 1)) * (size_t)(2 * chi) * ld;
   cplx* wk = d.work + (size_t)inst * (size_t)(2 * chi) * ld;
   cplx* lout = d.lbuf + (size_t)inst * (size_t)(2 * chi) * (2 * chi);
@@ -543,38 +551,66 @@ __global__ void __launch_bounds__(1024) k_lq(DqaDev d, int l) {
         }
       }
       __syncthreads();
-      // ---- trailing rows: one warp per row ----
-      for (int r = r_first + warp; r < mr; r += nwarp) {
-        const cplx* ysrc = src + (size_t)r * ld + p0;
-        cplx* ydst = wk + (size_t)r * ld + p0;
-        cplx acc[LQ_PB];
-#pragma unroll
-        for (int i = 0; i < LQ_PB; ++i) acc[i] = cmk(0.0, 0.0);
-        for (int c = lane; c < n; c += 32) {
-          const cplx y = ysrc[c];
-#pragma unroll
-          for (int i = 0; i < LQ_PB; ++i)
-            if (i < pb) acc[i] = cfmac(y, Vp[i * npad + c], acc[i]);  // y * conj(vbar_i) = (Y V)_i
+      // ---- trailing rows with FP64 tensor-core tiles: W = Y V (split over K), Z = W T, Y -= Z V^H ----
+      const int g = lane >> 2, t4 = lane & 3;
+      const int nrows = mr - r_first, ntr = (nrows + 7) >> 3;
+      int ks = nwarp / ntr;  // K-splits per row tile
+      if (ks < 1) ks = 1;
+      if (ks > LQ_MAXW / ntr) ks = LQ_MAXW / ntr > 0 ? LQ_MAXW / ntr : 1;
+      const int kchunk = (((n + ks - 1) / ks) + 3) & ~3;
+      for (int task = warp; task < ntr * ks; task += nwarp) {
+        const int rt = task / ks, kpart = task % ks;
+        const int r0 = r_first + rt * 8, kbeg = kpart * kchunk;
+        int kend = kbeg + kchunk;
+        if (kend > n) kend = n;
+        ZTile acc = ztile_zero();
+        if (kbeg < kend) {
+          const cplx* ysrc = src + p0 + kbeg;
+          const cplx* vsrc = Vp + kbeg;
+          const int klen = kend - kbeg;
+          warp_zgemm_8x8(
+              acc, klen,
+              [&](int row, int kk) { return (r0 + row < mr && kk < klen) ? ysrc[(size_t)(r0 + row) * ld + kk] : cmk(0.0, 0.0); },
+              [&](int kk, int col) { return (col < pb && kk < klen) ? cconj(vsrc[col * npad + kk]) : cmk(0.0, 0.0); });
         }
-#pragma unroll
-        for (int i = 0; i < LQ_PB; ++i) acc[i] = warp_sum(acc[i]);
-        // Z = W T : lane i computes Z_i
-        cplx zme = cmk(0.0, 0.0);
-#pragma unroll
-        for (int j = 0; j < LQ_PB; ++j)
-          if (j < pb && lane < pb && j <= lane) zme = cfma(acc[j], Tm[j * LQ_PB + lane], zme);
-        cplx z[LQ_PB];
-#pragma unroll
-        for (int i = 0; i < LQ_PB; ++i) {
-          z[i].x = __shfl_sync(DQA_FULL, zme.x, i);
-          z[i].y = __shfl_sync(DQA_FULL, zme.y, i);
+        cplx* wp = Wp + (size_t)task * 64;
+        wp[g * 8 + 2 * t4] = cmk(acc.r0, acc.i0);
+        wp[g * 8 + 2 * t4 + 1] = cmk(acc.r1, acc.i1);
+      }
+      __syncthreads();
+      // Z[row][i] = sum_j (sum_parts W[row][j]) T[j][i]
+      for (int o = tid; o < ntr * 64; o += nt) {
+        const int rt = o >> 6, row = (o >> 3) & 7, i = o & 7;
+        cplx z = cmk(0.0, 0.0);
+        for (int jj = 0; jj <= i && jj < pb; ++jj) {
+          cplx wsum = cmk(0.0, 0.0);
+          for (int kp2 = 0; kp2 < ks; ++kp2) wsum = cadd(wsum, Wp[(size_t)(rt * ks + kp2) * 64 + row * 8 + jj]);
+          z = cfma(wsum, Tm[jj * LQ_PB + i], z);
         }
-        for (int c = lane; c < n; c += 32) {
-          cplx y = ysrc[c];
-#pragma unroll
-          for (int i = 0; i < LQ_PB; ++i)
-            if (i < pb) y = cfms(z[i], Vp[i * npad + c], y);
-          ydst[c] = y;
+        Zs[o] = (i < pb) ? z : cmk(0.0, 0.0);
+      }
+      __syncthreads();
+      const int ntc = (n + 7) >> 3;
+      for (int tile = warp; tile < ntr * ntc; tile += nwarp) {
+        const int rt = tile / ntc, c0 = (tile % ntc) * 8;
+        const int r0 = r_first + rt * 8;
+        ZTile acc = ztile_zero();
+        const cplx* zt = Zs + rt * 64;
+        warp_zgemm_8x8(
+            acc, 8, [&](int row, int kk) { return zt[row * 8 + kk]; },
+            [&](int kk, int col) { return (kk < pb && c0 + col < n) ? Vp[kk * npad + c0 + col] : cmk(0.0, 0.0); });
+        const int r = r0 + g, c = c0 + 2 * t4;
+        if (r < mr) {
+          const cplx* ys = src + (size_t)r * ld + p0;
+          cplx* yd = wk + (size_t)r * ld + p0;
+          if (c < n) {
+            const cplx y = ys[c];
+            yd[c] = cmk(y.x - acc.r0, y.y - acc.i0);
+          }
+          if (c + 1 < n) {
+            const cplx y = ys[c + 1];
+            yd[c + 1] = cmk(y.x - acc.r1, y.y - acc.i1);
+          }
         }
       }
     }
@@ -624,7 +660,8 @@ __device__ __forceinline__ void rr_pair(int n, int round, int idx, int& p, int& 
 }
 
 #define JAC_UN 4
-__global__ void __launch_bounds__(256) k_jacobi(DqaDev d, int l, int mu, int p_step) {
+template <int RS>  // RS > 0: one pass per round, the pair's rows (li+8t, t<RS) stay in registers between dot and rotation
+__global__ void __launch_bounds__(512) k_jacobi(DqaDev d, int l, int mu, int p_step) {
   DQA_DYN_SMEM(smraw);
   const int inst = blockIdx.x, tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarp = nt >> 5;
   const int chi = d.chi;
@@ -653,6 +690,7 @@ __global__ void __launch_bounds__(256) k_jacobi(DqaDev d, int l, int mu, int p_s
   const int kp = k + (k & 1), half = kp >> 1;
   const int ppw = (half + nwarp - 1) / nwarp;  // pairs per warp and round
   const int grp = lane >> 3, li = lane & 7;
+  const int npass = (ppw + 3) >> 2;  // passes of 4 pairs per warp and round (<= 8)
   const double tol = sqrt((double)mr) * 2.220446049250313e-16, tol2 = tol * tol;
   double* nrm2 = sig;
   int sweeps = 0, converged = (k <= 1);
@@ -672,21 +710,34 @@ __global__ void __launch_bounds__(256) k_jacobi(DqaDev d, int l, int mu, int p_s
     __syncthreads();
     int myrot = 0;
     for (int round = 0; round < kp - 1; ++round) {
-      for (int u0 = 0; u0 < ppw; u0 += 4) {
-        const int pr = warp * ppw + u0 + grp;
+      // ---- phase 1: conj(x_p).x_q for every pair of this warp; lane li==pass of a group keeps it ----
+      cplx myg = cmk(0.0, 0.0);
+      int myp = 0, myq = 0;
+      bool myact = false;
+      cplx vp[RS > 0 ? RS : 1], vq[RS > 0 ? RS : 1];
+      for (int pass = 0; pass < npass; ++pass) {
+        const int u = pass * 4 + grp, pr = warp * ppw + u;
         int p = 0, q = 0;
-        bool act = (u0 + grp < ppw) && (pr < half);
+        bool act = (u < ppw) && (pr < half);
         if (act) {
           rr_pair(kp, round, pr, p, q);
           act = q < k;  // padded dummy column
         }
-        cplx* xp = L + p * ldl;
-        cplx* xq = L + q * ldl;
-        double a = 0.0, b = 0.0;
         cplx g = cmk(0.0, 0.0);
-        if (act) {
-          a = nrm2[p];
-          b = nrm2[q];
+        if (RS > 0) {
+          const cplx* xp = L + p * ldl;
+          const cplx* xq = L + q * ldl;
+#pragma unroll
+          for (int t = 0; t < (RS > 0 ? RS : 1); ++t) {
+            const int r = li + 8 * t;
+            const bool in = act && r < mr;
+            vp[t] = in ? xp[r] : cmk(0.0, 0.0);
+            vq[t] = in ? xq[r] : cmk(0.0, 0.0);
+            g = cfmac(vq[t], vp[t], g);
+          }
+        } else if (act) {
+          const cplx* xp = L + p * ldl;
+          const cplx* xq = L + q * ldl;
           for (int r = li; r < mr; r += 8) g = cfmac(xq[r], xp[r], g);  // conj(xp) * xq
         }
         g.x += __shfl_xor_sync(DQA_FULL, g.x, 4);
@@ -695,8 +746,23 @@ __global__ void __launch_bounds__(256) k_jacobi(DqaDev d, int l, int mu, int p_s
         g.y += __shfl_xor_sync(DQA_FULL, g.y, 2);
         g.x += __shfl_xor_sync(DQA_FULL, g.x, 1);
         g.y += __shfl_xor_sync(DQA_FULL, g.y, 1);
-        const double ag2 = cabs2(g);
-        if (act && ag2 > tol2 * a * b && ag2 > 0.0) {
+        if (li == pass) {
+          myg = g;
+          myact = act;
+        }
+        if (li == pass || RS > 0) {
+          myp = p;
+          myq = q;
+        }
+      }
+      // ---- phase 2: rotation parameters, one pair per lane (the FP64 chain is paid once per round) ----
+      double rc = 1.0, rsn = 0.0;
+      cplx rsph = cmk(0.0, 0.0), rcph = cmk(1.0, 0.0);
+      int rot = 0;
+      if (myact) {
+        const double a = nrm2[myp], b = nrm2[myq];
+        const double ag2 = cabs2(myg);
+        if (ag2 > tol2 * a * b && ag2 > 0.0) {
           const double rinv = rsqrt(ag2);
           const double ag = ag2 * rinv;
           const double zeta = 0.5 * (b - a) * rinv;
@@ -709,20 +775,46 @@ __global__ void __launch_bounds__(256) k_jacobi(DqaDev d, int l, int mu, int p_s
             tt = 0.5 / az;
           }
           tt = copysign(tt, zeta);
-          const double c = rsqrt(fma(tt, tt, 1.0));
-          const double sn = c * tt;
-          const cplx ph = cmk(g.x * rinv, -g.y * rinv);  // e^{-i phi}
-          const cplx sph = cscale(ph, sn), cph = cscale(ph, c);
-          for (int r = li; r < mr; r += 8) {
-            const cplx vp = xp[r], vq = xq[r];
-            xp[r] = cfms(sph, vq, cscale(vp, c));   // c*xp - s e^{-i phi} xq
-            xq[r] = cfma(cph, vq, cscale(vp, sn));  // s*xp + c e^{-i phi} xq
-          }
-          if (li == 0) {
-            const double na = a - tt * ag, nb = b + tt * ag;
-            nrm2[p] = na > 0.0 ? na : 0.0;
-            nrm2[q] = nb > 0.0 ? nb : 0.0;
-            myrot++;
+          rc = rsqrt(fma(tt, tt, 1.0));
+          rsn = rc * tt;
+          const cplx ph = cmk(myg.x * rinv, -myg.y * rinv);  // e^{-i phi}
+          rsph = cscale(ph, rsn);
+          rcph = cscale(ph, rc);
+          rot = 1;
+          const double na = a - tt * ag, nb = b + tt * ag;
+          nrm2[myp] = na > 0.0 ? na : 0.0;
+          nrm2[myq] = nb > 0.0 ? nb : 0.0;
+          myrot++;
+        }
+      }
+      // ---- phase 3: every group applies its pair's rotation, pass by pass ----
+      for (int pass = 0; pass < npass; ++pass) {
+        const int src = (lane & ~7) | pass;
+        const int dr = __shfl_sync(DQA_FULL, rot, src);
+        if (!__any_sync(DQA_FULL, dr)) continue;  // warp-uniform
+        const int p = RS > 0 ? myp : __shfl_sync(DQA_FULL, myp, src);
+        const int q = RS > 0 ? myq : __shfl_sync(DQA_FULL, myq, src);
+        const double c = __shfl_sync(DQA_FULL, rc, src), sn = __shfl_sync(DQA_FULL, rsn, src);
+        const cplx sph = cmk(__shfl_sync(DQA_FULL, rsph.x, src), __shfl_sync(DQA_FULL, rsph.y, src));
+        const cplx cph = cmk(__shfl_sync(DQA_FULL, rcph.x, src), __shfl_sync(DQA_FULL, rcph.y, src));
+        if (dr) {
+          cplx* xp = L + p * ldl;
+          cplx* xq = L + q * ldl;
+          if (RS > 0) {
+#pragma unroll
+            for (int t = 0; t < (RS > 0 ? RS : 1); ++t) {
+              const int r = li + 8 * t;
+              if (r < mr) {
+                xp[r] = cfms(sph, vq[t], cscale(vp[t], c));   // c*xp - s e^{-i phi} xq
+                xq[r] = cfma(cph, vq[t], cscale(vp[t], sn));  // s*xp + c e^{-i phi} xq
+              }
+            }
+          } else {
+            for (int r = li; r < mr; r += 8) {
+              const cplx a_ = xp[r], b_ = xq[r];
+              xp[r] = cfms(sph, b_, cscale(a_, c));
+              xq[r] = cfma(cph, b_, cscale(a_, sn));
+            }
           }
         }
       }

@@ -135,6 +135,35 @@ int dqa_measure_fp64_peak(dqa_t* h, double* tflops);
 
 const char* dqa_version(void);
 
+/* ---- op-level API: the reference's lib/tenn.py functions on dense site tensors --------------------
+ * Host buffers in and out (complex128 interleaved, row-major, the reference's array layouts); the device
+ * scratch is caller-owned and handed over once (dqa_ops_create).  An op that needs more scratch than the
+ * context has returns DQA_ELIMIT and says how much.  The driver's hot loop does not use these. */
+typedef struct dqa_ops dqa_ops_t;
+int dqa_ops_create(dqa_ops_t** ctx, void* device_scratch, size_t bytes, int device, void* stream);
+void dqa_ops_destroy(dqa_ops_t* ctx);
+const char* dqa_ops_last_error(const dqa_ops_t* ctx);
+/* contract_mps_mpo_single_site (lib/tenn.py:67-81): A (al,2,ar) x W (wl,wr,2,2) -> out (al*wl, 2, ar*wr) */
+int dqa_op_contract_site(dqa_ops_t* ctx, const double* A, int al, int ar, const double* W, int wl, int wr, double* out);
+/* braket(bra, ket) (lib/tenn.py:93-109; conjugates ket): packed site tensors, bond arrays of n+1 entries -> env (rb x rk) */
+int dqa_op_braket(dqa_ops_t* ctx, int n, const int32_t* bra_bonds, const double* bra, const int32_t* ket_bonds, const double* ket, double* env);
+/* qr_stabilized(x) (lib/tenn.py:294-304), sgn(0):=+1: X (m x n) -> Q (m x min), R (min x n) */
+int dqa_op_qr_stabilized(dqa_ops_t* ctx, const double* X, int m, int n, double* Q, double* R);
+/* right_canonize_twosites(A, B) (lib/tenn.py:152-176): A (al,2,bl), B (bl,2,br) -> A' (al,2,kq) normalised, B' (kq,2,br) */
+int dqa_op_right_canonize_twosites(dqa_ops_t* ctx, const double* A, int al, const double* B, int bl, int br, double* Anew, double* Bnew, int* kq);
+/* svd_truncated (lib/tenn.py:307-405): cutoff modes 1..6, max_bond (<=0: none), absorb -1/0/1/2(None), renorm; buffers sized for
+ * k = min(m,n); the leading n_chi columns of U (ld k) / rows of Vh are the result */
+int dqa_op_svd_truncated(dqa_ops_t* ctx, const double* X, int m, int n, double cutoff, int cutoff_mode, int max_bond, int absorb, int renorm,
+                         double* U, double* S, double* Vh, int* n_chi);
+/* compress_normalize_onesite(A, A_next, max_bd) (lib/tenn.py:229-252): A (l,2,r), A_next (r,2,r2) -> A' (l,2,n_chi), A_next' (n_chi,2,r2) */
+int dqa_op_compress_onesite(dqa_ops_t* ctx, const double* A, int l, int r, const double* Anext, int r2, int max_bd, double* Aout,
+                            double* Anext_out, int* n_chi);
+/* x /= |x|_F (lib/tenn.py:259) */
+int dqa_op_normalize(dqa_ops_t* ctx, double* x, long n);
+/* compute_loss of an external packed MPS with n_sites - n_phys trailing ancilla sites (lib/dQA_loss.py:28-78, dQA_mps.py:68-81) */
+int dqa_op_energy(dqa_ops_t* ctx, int n_sites, int n_phys, int n_xi, const int32_t* bonds, const double* mps, const int8_t* xi,
+                  const double* fxft, double* eps);
+
 #ifdef __cplusplus
 }
 #endif

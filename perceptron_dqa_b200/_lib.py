@@ -72,6 +72,18 @@ _SIGS = {
     "dqa_profile_end": ([_P, _P, _P], C.c_int),
     "dqa_measure_fp64_peak": ([_P, C.POINTER(C.c_double)], C.c_int),
     "dqa_version": ([], C.c_char_p),
+    "dqa_ops_create": ([C.POINTER(_P), _P, C.c_size_t, C.c_int, _P], C.c_int),
+    "dqa_ops_destroy": ([_P], None),
+    "dqa_ops_last_error": ([_P], C.c_char_p),
+    "dqa_op_contract_site": ([_P, _P, C.c_int, C.c_int, _P, C.c_int, C.c_int, _P], C.c_int),
+    "dqa_op_braket": ([_P, C.c_int, _P, _P, _P, _P, _P], C.c_int),
+    "dqa_op_qr_stabilized": ([_P, _P, C.c_int, C.c_int, _P, _P], C.c_int),
+    "dqa_op_right_canonize_twosites": ([_P, _P, C.c_int, _P, C.c_int, C.c_int, _P, _P, C.POINTER(C.c_int)], C.c_int),
+    "dqa_op_svd_truncated": ([_P, _P, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P,
+                              C.POINTER(C.c_int)], C.c_int),
+    "dqa_op_compress_onesite": ([_P, _P, C.c_int, C.c_int, _P, C.c_int, C.c_int, _P, _P, C.POINTER(C.c_int)], C.c_int),
+    "dqa_op_normalize": ([_P, _P, C.c_long], C.c_int),
+    "dqa_op_energy": ([_P, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P], C.c_int),
 }
 EXPORTS = tuple(_SIGS)
 
@@ -291,3 +303,117 @@ class Plan:
         v = C.c_double()
         self._ck(self.lib.dqa_measure_fp64_peak(self._h, C.byref(v)))
         return v.value
+
+
+class Ops:
+    """Op-level context (include/dqa.h, "op-level API"): the reference's lib/tenn.py functions on dense
+    site tensors, computed on the GPU.  Owns nothing but a caller-allocated device scratch."""
+
+    def __init__(self, scratch_bytes=256 << 20, device=0, stream=None, lib=None, workspace=None):
+        self.lib = lib or load()
+        alloc = workspace or _torch_workspace
+        self._owner, ptr = alloc(scratch_bytes, device)
+        self._h = _P()
+        rc = self.lib.dqa_ops_create(C.byref(self._h), ptr, scratch_bytes, device, stream)
+        if rc != 0:
+            raise DqaError(rc, self.lib.dqa_ops_last_error(self._h).decode() if self._h else "dqa_ops_create failed")
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise (DqaNumericError if rc == -4 else DqaError)(rc, self.lib.dqa_ops_last_error(self._h).decode())
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.dqa_ops_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @staticmethod
+    def _c(a):
+        return np.ascontiguousarray(a, dtype=np.complex128)
+
+    def contract_site(self, a, w):
+        a, w = self._c(a), self._c(w)
+        al, _, ar = a.shape
+        wl, wr = w.shape[0], w.shape[1]
+        out = np.empty((al * wl, 2, ar * wr), dtype=np.complex128)
+        self._ck(self.lib.dqa_op_contract_site(self._h, _ptr(a), al, ar, _ptr(w), wl, wr, _ptr(out)))
+        return out
+
+    @staticmethod
+    def _pack(mps):
+        bonds = np.array([mps[0].shape[0]] + [t.shape[2] for t in mps], dtype=np.int32)
+        flat = np.concatenate([np.ascontiguousarray(t, dtype=np.complex128).ravel() for t in mps])
+        return bonds, flat
+
+    def braket(self, bra, ket):
+        bb, bf = self._pack(bra)
+        kb, kf = self._pack(ket)
+        out = np.empty((int(bb[-1]), int(kb[-1])), dtype=np.complex128)
+        self._ck(self.lib.dqa_op_braket(self._h, len(bra), _ptr(bb), _ptr(bf), _ptr(kb), _ptr(kf), _ptr(out)))
+        return out
+
+    def qr_stabilized(self, x):
+        x = self._c(x)
+        m, n = x.shape
+        k = min(m, n)
+        q = np.empty((m, k), dtype=np.complex128)
+        r = np.empty((k, n), dtype=np.complex128)
+        self._ck(self.lib.dqa_op_qr_stabilized(self._h, _ptr(x), m, n, _ptr(q), _ptr(r)))
+        return q, r
+
+    def right_canonize_twosites(self, a, b):
+        a, b = self._c(a), self._c(b)
+        al, bl, br = a.shape[0], b.shape[0], b.shape[2]
+        kq = min(2 * br, bl)
+        an = np.empty((al, 2, kq), dtype=np.complex128)
+        bn = np.empty((kq, 2, br), dtype=np.complex128)
+        k = C.c_int()
+        self._ck(self.lib.dqa_op_right_canonize_twosites(self._h, _ptr(a), al, _ptr(b), bl, br, _ptr(an), _ptr(bn), C.byref(k)))
+        return an, bn
+
+    def svd_truncated(self, x, cutoff=-1.0, cutoff_mode=3, max_bond=-1, absorb=0, renorm=0):
+        x = self._c(x)
+        m, n = x.shape
+        k = min(m, n)
+        u = np.empty((m, k), dtype=np.complex128)
+        s = np.empty(k, dtype=np.float64)
+        vh = np.empty((k, n), dtype=np.complex128)
+        nc = C.c_int()
+        ab = 2 if absorb is None else int(absorb)
+        self._ck(self.lib.dqa_op_svd_truncated(self._h, _ptr(x), m, n, float(cutoff), int(cutoff_mode), int(max_bond), ab, int(renorm),
+                                               _ptr(u), _ptr(s), _ptr(vh), C.byref(nc)))
+        c = nc.value
+        return u[:, :c].copy(), s[:c].copy(), vh[:c].copy()
+
+    def compress_onesite(self, a, a_next, max_bd):
+        a, a_next = self._c(a), self._c(a_next)
+        l, _, r = a.shape
+        r2 = a_next.shape[2]
+        k = min(2 * l, r)
+        ao = np.empty(2 * l * k, dtype=np.complex128)
+        no = np.empty(k * 2 * r2, dtype=np.complex128)
+        nc = C.c_int()
+        self._ck(self.lib.dqa_op_compress_onesite(self._h, _ptr(a), l, r, _ptr(a_next), r2, int(max_bd), _ptr(ao), _ptr(no), C.byref(nc)))
+        c = nc.value
+        return ao[: 2 * l * c].reshape(l, 2, c).copy(), no[: c * 2 * r2].reshape(c, 2, r2).copy()
+
+    def normalize(self, x):
+        x = self._c(x).copy()
+        self._ck(self.lib.dqa_op_normalize(self._h, _ptr(x), x.size))
+        return x
+
+    def energy(self, mps, xi, fxft, n_ancilla=0):
+        bonds, flat = self._pack(mps)
+        xi = np.ascontiguousarray(xi, dtype=np.int8)
+        fx = np.ascontiguousarray(fxft, dtype=np.complex128)
+        out = np.empty(1, dtype=np.complex128)
+        n_phys = len(mps) - n_ancilla
+        assert xi.shape[1] == n_phys and fx.shape[0] == n_phys + 1
+        self._ck(self.lib.dqa_op_energy(self._h, len(mps), n_phys, xi.shape[0], _ptr(bonds), _ptr(flat), _ptr(xi), _ptr(fx), _ptr(out)))
+        return complex(out[0])

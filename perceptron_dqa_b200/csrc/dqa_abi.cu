@@ -11,7 +11,14 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <vector>
+
+#ifdef DQA_EMUL
+#define OPS_THREADS 64
+#else
+#define OPS_THREADS 1024
+#endif
 
 struct dqa_handle {
   dqa_config cfg;
@@ -710,3 +717,5 @@ extern "C" int dqa_measure_fp64_peak(dqa_t* h, double* tflops) {
   *tflops = best;
   return DQA_OK;
 }
+
+#include "dqa_ops_abi.cuh"

@@ -929,24 +929,33 @@ __global__ void k_mixer(DqaDev d, double cb, double sb) {
 // ---------------------------------------------------------------------------------
 __host__ __device__ inline size_t energy_smem(int chi) { return sizeof(cplx) * (size_t)4 * chi * chi; }
 
-__global__ void __launch_bounds__(256) k_energy(DqaDev d) {
-  DQA_DYN_SMEM(smraw);
-  const int k = blockIdx.x, mu = blockIdx.y, inst = blockIdx.z, tid = threadIdx.x;
+// where the site tensors of one MPS live: the plan's padded layout or a packed external MPS
+struct EnergyView {
+  const cplx* base;   // first site
+  const long* off;    // per-site element offsets (NULL: site i at i * 2*chi*chi, row stride chi)
+  const int* bond;    // n_sites+1 bond dimensions
+  int n_sites;        // sites swept
+  int n_phys;         // sites that carry the phase operator; trailing ones (ancillas) carry the identity
+  int chi;            // capacity of the shared-memory environments
+};
+
+// T = <psi| prod_{i<n_phys} diag_s(ph_i(s)) |psi> for one (mu,k): transfer-matrix sweep with
+// FP64 tensor-core tiles.  smem: E, E2, W0, W1 (chi*chi each).
+__device__ __forceinline__ cplx energy_sweep(const EnergyView& v, const uint8_t* hb, cplx wk, cplx* smem) {
+  const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5, g = lane >> 2, t = lane & 3;
-  const int chi = d.chi;
+  const int chi = v.chi;
   const size_t rsz = (size_t)chi * chi;
-  cplx* E = (cplx*)smraw;
+  cplx* E = smem;
   cplx* E2 = E + rsz;
   cplx* W0 = E2 + rsz;
   cplx* W1 = W0 + rsz;
-  const int* bond = d.bond + inst * (d.N + 1);
-  const uint8_t* hb = d.hbit + ((size_t)inst * d.n_xi + mu) * d.N;
-  const cplx wk = d.phase[k];  // exp(i pi q / D) with q = k*e, e = 2
   if (tid == 0) E[0] = cmk(1.0, 0.0);
   __syncthreads();
-  for (int i = 0; i < d.N; ++i) {
-    const int bl = bond[i], br = bond[i + 1];
-    const cplx* a = d.mps + ((size_t)inst * d.N + i) * (2 * rsz);
+  for (int i = 0; i < v.n_sites; ++i) {
+    const int bl = v.bond[i], br = v.bond[i + 1];
+    const cplx* a = v.off ? v.base + v.off[i] : v.base + (size_t)i * (2 * rsz);
+    const int lda = v.off ? br : chi;
     const int tr = (bl + 7) >> 3, tc = (br + 7) >> 3;
     // phase 1 (DMMA): W_s[c,b] = sum_a E[a,c] A[a,s,b], both s
     for (int tile = warp; tile < 2 * tr * tc; tile += nwarp) {
@@ -955,7 +964,7 @@ __global__ void __launch_bounds__(256) k_energy(DqaDev d) {
       warp_zgemm_8x8(
           acc, bl,
           [&](int row, int kk) { return (c0 + row < bl && kk < bl) ? E[kk * bl + c0 + row] : cmk(0.0, 0.0); },
-          [&](int kk, int col) { return (kk < bl && b0 + col < br) ? a[(kk * 2 + s) * chi + b0 + col] : cmk(0.0, 0.0); });
+          [&](int kk, int col) { return (kk < bl && b0 + col < br) ? a[((size_t)kk * 2 + s) * lda + b0 + col] : cmk(0.0, 0.0); });
       cplx* W = s ? W1 : W0;
       const int c = c0 + g, b = b0 + 2 * t;
       if (c < bl) {
@@ -974,8 +983,8 @@ __global__ void __launch_bounds__(256) k_energy(DqaDev d) {
         warp_zgemm_8x8(
             acc, bl,
             [&](int row, int kk) { return (b0 + row < br && kk < bl) ? W[kk * br + b0 + row] : cmk(0.0, 0.0); },
-            [&](int kk, int col) { return (kk < bl && d0 + col < br) ? cconj(a[(kk * 2 + s) * chi + d0 + col]) : cmk(0.0, 0.0); });
-        const cplx ph = (hb[i] ^ s) ? wk : cmk(1.0, 0.0);
+            [&](int kk, int col) { return (kk < bl && d0 + col < br) ? cconj(a[((size_t)kk * 2 + s) * lda + d0 + col]) : cmk(0.0, 0.0); });
+        const cplx ph = (i < v.n_phys && (hb[i] ^ s)) ? wk : cmk(1.0, 0.0);
         out0 = cfma(ph, cmk(acc.r0, acc.i0), out0);
         out1 = cfma(ph, cmk(acc.r1, acc.i1), out1);
       }
@@ -990,7 +999,53 @@ __global__ void __launch_bounds__(256) k_energy(DqaDev d) {
     E = E2;
     E2 = t2;
   }
-  if (tid == 0) d.tmk[((size_t)inst * d.n_xi + mu) * d.kh + k] = E[0];
+  return E[0];
+}
+
+__global__ void __launch_bounds__(256) k_energy(DqaDev d) {
+  DQA_DYN_SMEM(smraw);
+  const int k = blockIdx.x, mu = blockIdx.y, inst = blockIdx.z;
+  EnergyView v;
+  v.base = d.mps + (size_t)inst * d.N * (size_t)(2 * d.chi * d.chi);
+  v.off = nullptr;
+  v.bond = d.bond + inst * (d.N + 1);
+  v.n_sites = d.N;
+  v.n_phys = d.N;
+  v.chi = d.chi;
+  const cplx r = energy_sweep(v, d.hbit + ((size_t)inst * d.n_xi + mu) * d.N, d.phase[k], (cplx*)smraw);
+  if (threadIdx.x == 0) d.tmk[((size_t)inst * d.n_xi + mu) * d.kh + k] = r;
+}
+
+// mydQA_ancilla.compute_loss (lib/dQA_loss.py:67-78): an external, packed MPS of n_sites >= n_phys sites
+// (trailing ancilla sites carry the identity), bonds <= chi.  grid (kh, n_xi); tmk [n_xi][kh].
+__global__ void __launch_bounds__(256) k_energy_ext(const cplx* mps, const long* off, const int* bond, int n_sites, int n_phys,
+                                                    int chi, const uint8_t* hbit, const cplx* phase, int kh, cplx* tmk) {
+  DQA_DYN_SMEM(smraw);
+  const int k = blockIdx.x, mu = blockIdx.y;
+  EnergyView v;
+  v.base = mps;
+  v.off = off;
+  v.bond = bond;
+  v.n_sites = n_sites;
+  v.n_phys = n_phys;
+  v.chi = chi;
+  const cplx r = energy_sweep(v, hbit + (size_t)mu * n_phys, phase[k], (cplx*)smraw);
+  if (threadIdx.x == 0) tmk[(size_t)mu * kh + k] = r;
+}
+
+// eps = (1/n_phys) sum_mu [...] for the external-MPS variant (same combination as k_energy_reduce)
+__global__ void k_energy_ext_reduce(const cplx* tmk, const cplx* gk, int n_xi, int kh, int D, int n_phys, cplx* out) {
+  const int lane = threadIdx.x;
+  cplx acc = cmk(0.0, 0.0);
+  const int n = n_xi * kh;
+  for (int i = lane; i < n; i += 32) {
+    const int k = i % kh;
+    const cplx t = tmk[i];
+    acc = cfma(gk[k], t, acc);
+    if (k > 0 && 2 * k != D) acc = cfmac(gk[D - k], t, acc);
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) out[0] = cscale(acc, 1.0 / n_phys);
 }
 
 // eps = (1/N) sum_mu [ sum_{k<=D/2} g_k T_k + sum_{0<k<D/2} g_{D-k} conj(T_k) ]; one warp per instance

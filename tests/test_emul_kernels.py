@@ -49,3 +49,41 @@ def test_batch(factory):
 
 def test_teacher_forced_n12_one_substep(factory):
     ps.check_teacher_forced(factory, "c1_n12_chi10", max_snaps=1)
+
+
+# ---- op-level API (lib/tenn.py functions) on the emulator -------------------------------------------
+@pytest.fixture(scope="module")
+def tenn_emul():
+    import emul_lib
+    from perceptron_dqa_b200 import tenn
+    from perceptron_dqa_b200._lib import Ops
+
+    o = Ops(scratch_bytes=64 << 20, lib=emul_lib.load(), workspace=emul_lib.numpy_workspace)
+    tenn.set_ops(o)
+    yield tenn, o
+    tenn.set_ops(None)
+
+
+def test_ops_apply_braket_qr(tenn_emul):
+    import ops_suite as os_
+
+    T, _ = tenn_emul
+    os_.check_apply_and_braket(T)
+    os_.check_qr(T)
+
+
+def test_ops_canonize_svd_compress(tenn_emul):
+    import ops_suite as os_
+
+    T, _ = tenn_emul
+    os_.check_right_canonize(T)
+    os_.check_svd_truncated(T)
+    os_.check_compress(T)
+
+
+def test_ops_dense_substep_and_energy(tenn_emul):
+    import ops_suite as os_
+
+    T, o = tenn_emul
+    os_.check_dense_substep_equals_reference(T)
+    os_.check_energy_ext(T, o)

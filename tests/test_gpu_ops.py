@@ -1,0 +1,76 @@
+"""GPU: the op-level API (perceptron_dqa_b200.tenn = the reference's lib/tenn.py names) and the ancilla
+loss (lib/dQA_loss.py) through libdqa.so's op kernels."""
+import numpy as np
+import pytest
+
+import dqa_oracle as O
+import ops_suite as os_
+from helpers import golden, snapshots
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def T():
+    from perceptron_dqa_b200 import tenn
+
+    return tenn
+
+
+def test_apply_mpsmpo_and_braket(T):
+    os_.check_apply_and_braket(T)
+
+
+def test_qr_stabilized(T):
+    os_.check_qr(T)
+
+
+def test_right_canonize(T):
+    os_.check_right_canonize(T)
+
+
+def test_svd_truncated_all_modes(T):
+    os_.check_svd_truncated(T)
+
+
+def test_compress_svd_normalized(T):
+    os_.check_compress(T)
+
+
+def test_dense_substep_through_op_api(T):
+    os_.check_dense_substep_equals_reference(T)
+
+
+def test_energy_external_mps_with_ancillas(T):
+    os_.check_energy_ext(T, T.ops())
+
+
+def test_mydqa_ancilla_class():
+    """lib/dQA_loss.py:53-84: compute_loss with ancillas and flip_endian; run/single_step forbidden."""
+    from perceptron_dqa_b200.dQA_loss import mydQA_ancilla
+
+    g = golden("n7_chi4")
+    _p, _mu, _pre, post = snapshots(g)[1]
+    obj = mydQA_ancilla(g["xi"], P=int(g["P"]), dt=float(g["dt"]), n_ancilla=0)
+    assert abs(obj.compute_loss(post) - O.compute_loss(post, g["xi"], g["fxft"])) < 1e-13
+    flipped = mydQA_ancilla(g["xi"], P=int(g["P"]), dt=float(g["dt"]), n_ancilla=0, flip_endian=True)
+    want = O.compute_loss(post, g["xi"][:, ::-1], g["fxft"])
+    assert abs(flipped.compute_loss(post) - want) < 1e-13
+    with pytest.raises(Exception):
+        obj.run()
+    with pytest.raises(Exception):
+        obj.single_step()
+
+
+def test_dense_path_at_reference_sizes(T):
+    """One C1 sub-step (N=12, chi=10) the reference's way -- QR of (2*r x 130)-shaped direct-sum blocks,
+    SVD of (20 x <=130) matrices -- against the stored reference state."""
+    from perceptron_dqa_b200.dQA_utils import PerceptronHamiltonian
+
+    g = golden("c1_n12_chi10")
+    p, mu, pre, post = snapshots(g)[3]
+    psi = T.apply_mpsmpo(pre, PerceptronHamiltonian.make_Uz(12, g["Uk_FT"][:, p], g["xi"][mu]))
+    assert psi[5].shape == (130, 2, 130)
+    psi = T.compress_svd_normalized(T.right_canonize(psi, 1), 10)
+    assert [t.shape for t in psi] == [t.shape for t in post]
+    assert abs(O.fidelity_defect(psi, post)) < 1e-11

@@ -99,19 +99,22 @@ __global__ void k_init_plus(DqaDev d) {
 // column with no block barrier at all (column j only needs reflectors j..0).
 // shared memory: M (2chi x chi, col-major; column k ends up holding reflector v_k) | tau | beta
 // ---------------------------------------------------------------------------------
-__host__ __device__ inline size_t sector_qr_smem(int chi) {
-  return sizeof(cplx) * ((size_t)2 * chi * chi + chi) + sizeof(double) * chi;
+__host__ __device__ inline int sector_qr_maxs(int chi) { return chi <= 8 ? 2 : (chi <= 16 ? 4 : (chi <= 32 ? 8 : 12)); }
+__host__ __device__ inline size_t sector_qr_smem(int chi) {  // M has 8*MAXS rows so every register slot has a row
+  return sizeof(cplx) * ((size_t)8 * sector_qr_maxs(chi) * chi + chi) + sizeof(double) * chi;
 }
 
-// All three per-column routines are specialised on T0 = k>>3, the first register slot that still
-// holds live rows (rows <= k are finished), so finished slots cost no instructions.
-template <int MAXS, int T0>
+// Reflector k is stored in shared memory as the FULL vector over the live register slots
+// (0 above row k, 1 at row k, the scaled entries below, 0 beyond row m-1), so applying it needs no
+// per-row conditions: w = sum conj(v) col, col -= tau w v.  Slots t < k>>3 hold only finished rows and
+// are skipped by jumping into the unrolled slot sequence (fall-through switch: one copy of the code).
+template <int MAXS>
 __device__ __forceinline__ void sqr_publish(cplx (&col)[MAXS], int k, int m, int j, int li, cplx* Mk, cplx* tau, double* betas) {
   // executed by every lane of the warp that contains group k; only group k == j stores
   double ss = 0.0;
   cplx alpha = cmk(0.0, 0.0);
 #pragma unroll
-  for (int t = T0; t < MAXS; ++t) {
+  for (int t = 0; t < MAXS; ++t) {
     const int row = li + 8 * t;
     if (row > k && row < m) ss += cabs2(col[t]);
     if (row == k) alpha = col[t];
@@ -131,13 +134,18 @@ __device__ __forceinline__ void sqr_publish(cplx (&col)[MAXS], int k, int m, int
   cplx t_, scal;
   householder_gen(alpha, ss, beta, t_, scal);
 #pragma unroll
-  for (int t = T0; t < MAXS; ++t) {
+  for (int t = 0; t < MAXS; ++t) {
     const int row = li + 8 * t;
+    cplx v = cmk(0.0, 0.0);
     if (row > k && row < m) {
       col[t] = cmul(col[t], scal);
-      Mk[row] = col[t];
+      v = col[t];
     }
-    if (row == k) col[t] = cmk(beta, 0.0);
+    if (row == k) {
+      col[t] = cmk(beta, 0.0);
+      v = cmk(1.0, 0.0);
+    }
+    if (row >= (k & ~7)) Mk[row] = v;
   }
   if (li == 0) {
     tau[k] = t_;
@@ -145,20 +153,25 @@ __device__ __forceinline__ void sqr_publish(cplx (&col)[MAXS], int k, int m, int
   }
 }
 
-// col <- (I - tk v v^H) col for the group's column, v = reflector k (rows > k in shared memory, v_k = 1)
-template <int MAXS, int T0>
-__device__ __forceinline__ void sqr_apply(cplx (&col)[MAXS], const cplx* vk, cplx tk, int k, int m, int li, bool act) {
+#define SQR_DOT(T)                          \
+  case T:                                   \
+    if (T < MAXS) {                         \
+      v[T < MAXS ? T : 0] = vk[li + 8 * T]; \
+      w = cfmac(col[T < MAXS ? T : 0], v[T < MAXS ? T : 0], w); \
+    }
+#define SQR_UPD(T) \
+  case T:          \
+    if (T < MAXS) col[T < MAXS ? T : 0] = cfms(tw, v[T < MAXS ? T : 0], col[T < MAXS ? T : 0]);
+
+// col <- (I - tk v v^H) col for the group's column; t0 = first live slot of reflector v
+template <int MAXS>
+__device__ __forceinline__ void sqr_apply(cplx (&col)[MAXS], const cplx* vk, cplx tk, int t0, int li, bool act) {
   cplx v[MAXS];
   cplx w = cmk(0.0, 0.0);
-#pragma unroll
-  for (int t = T0; t < MAXS; ++t) {
-    const int row = li + 8 * t;
-    v[t] = cmk(0.0, 0.0);
-    if (act && row > k && row < m) {
-      v[t] = vk[row];
-      w = cfmac(col[t], v[t], w);  // col * conj(v)
-    }
-    if (act && row == k) w = cadd(w, col[t]);
+  switch (t0) {  // fall through on purpose
+    SQR_DOT(0) SQR_DOT(1) SQR_DOT(2) SQR_DOT(3) SQR_DOT(4) SQR_DOT(5)
+    SQR_DOT(6) SQR_DOT(7) SQR_DOT(8) SQR_DOT(9) SQR_DOT(10) SQR_DOT(11)
+    default: break;
   }
   w.x += __shfl_xor_sync(DQA_FULL, w.x, 4);
   w.y += __shfl_xor_sync(DQA_FULL, w.y, 4);
@@ -168,34 +181,21 @@ __device__ __forceinline__ void sqr_apply(cplx (&col)[MAXS], const cplx* vk, cpl
   w.y += __shfl_xor_sync(DQA_FULL, w.y, 1);
   if (act) {
     const cplx tw = cmul(tk, w);
-#pragma unroll
-    for (int t = T0; t < MAXS; ++t) {
-      const int row = li + 8 * t;
-      if (row == k) col[t] = csub(col[t], tw);
-      if (row > k && row < m) col[t] = cfms(tw, v[t], col[t]);
+    switch (t0) {  // fall through on purpose
+      SQR_UPD(0) SQR_UPD(1) SQR_UPD(2) SQR_UPD(3) SQR_UPD(4) SQR_UPD(5)
+      SQR_UPD(6) SQR_UPD(7) SQR_UPD(8) SQR_UPD(9) SQR_UPD(10) SQR_UPD(11)
+      default: break;
     }
   }
 }
 
-// dispatch on the first live slot rounded down to a multiple of 4 (3 code variants at most: the
-// fully specialised 12-way switch overflowed the instruction cache and ran slower)
-#define SQR_CASE(T0, CALL) \
-  case T0:                 \
-    if (T0 < MAXS) { CALL(T0 < MAXS ? T0 : 0); } \
-    break;
-#define SQR_DISPATCH(slot, CALL)                               \
-  switch ((slot) & ~3) {                                        \
-    SQR_CASE(0, CALL) SQR_CASE(4, CALL) SQR_CASE(8, CALL)       \
-    default: break;                                             \
-  }
-
 template <int MAXS>
-__global__ void __launch_bounds__(512) k_sector_qr(DqaDev d, int n, int mu) {
+__global__ void __launch_bounds__(MAXS <= 8 ? 256 : 512, MAXS <= 4 ? 4 : (MAXS == 8 ? 3 : 1)) k_sector_qr(DqaDev d, int n, int mu) {
   DQA_DYN_SMEM(smraw);
   const int y = blockIdx.x, inst = blockIdx.y;
   const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarp = nt >> 5;
   const int j = tid >> 3, li = tid & 7;  // column owned by this 8-lane group, lane in group
-  const int chi = d.chi, ldm = 2 * chi;
+  const int chi = d.chi, ldm = 8 * MAXS, ldq = 2 * chi;
   cplx* M = (cplx*)smraw;
   cplx* tau = M + (size_t)ldm * chi;
   double* betas = (double*)(tau + chi);
@@ -247,18 +247,14 @@ __global__ void __launch_bounds__(512) k_sector_qr(DqaDev d, int n, int mu) {
     col[t] = (has && row < m) ? M[row + j * ldm] : cmk(0.0, 0.0);
   }
   __syncthreads();  // M is reused for the reflectors from here on
-  if (warp == 0 && q > 0) sqr_publish<MAXS, 0>(col, 0, m, j, li, M, tau, betas);
+  if (warp == 0 && q > 0) sqr_publish<MAXS>(col, 0, m, j, li, M, tau, betas);
   __syncthreads();
   for (int k = 0; k < q; ++k) {
-    const cplx tk = cconj(tau[k]);  // H^H is applied
-    const bool act = has && j > k && (tk.x != 0.0 || tk.y != 0.0);
-    const cplx* vk = M + k * ldm;
-#define SQR_CALL_APPLY(T0) sqr_apply<MAXS, T0>(col, vk, tk, k, m, li, act)
-    SQR_DISPATCH(k >> 3, SQR_CALL_APPLY)
-    if (k + 1 < q && warp == ((k + 1) >> 2)) {
-      const int k1 = k + 1;
-#define SQR_CALL_PUB(T0) sqr_publish<MAXS, T0>(col, k1, m, j, li, M + k1 * ldm, tau, betas)
-      SQR_DISPATCH(k1 >> 3, SQR_CALL_PUB)
+    if (4 * warp + 3 > k) {  // warps whose four columns are all finished (j <= k) have nothing to do
+      const cplx tk = cconj(tau[k]);  // H^H is applied
+      const bool act = has && j > k && (tk.x != 0.0 || tk.y != 0.0);
+      sqr_apply<MAXS>(col, M + k * ldm, tk, k >> 3, li, act);
+      if (k + 1 < q && warp == ((k + 1) >> 2)) sqr_publish<MAXS>(col, k + 1, m, j, li, M + (k + 1) * ldm, tau, betas);
     }
     __syncthreads();
   }
@@ -289,9 +285,7 @@ __global__ void __launch_bounds__(512) k_sector_qr(DqaDev d, int n, int mu) {
     for (int i = imax; i >= 0; --i) {  // warp-uniform trip count
       const cplx ti = tau[i];
       const bool act = (j < q) && (i <= j) && (ti.x != 0.0 || ti.y != 0.0);
-      const cplx* vi = M + i * ldm;
-#define SQR_CALL_Q(T0) sqr_apply<MAXS, T0>(qc, vi, ti, i, m, li, act)
-      SQR_DISPATCH(i >> 3, SQR_CALL_Q)
+      sqr_apply<MAXS>(qc, M + i * ldm, ti, i >> 3, li, act);
     }
     if (j < q) {
       cplx* qout = d.qbuf + ((size_t)inst * d.nsec_total + dqa_secbase(d.N, n) + y) * (2 * rsz);
@@ -299,7 +293,7 @@ __global__ void __launch_bounds__(512) k_sector_qr(DqaDev d, int n, int mu) {
 #pragma unroll
       for (int t = 0; t < MAXS; ++t) {
         const int row = li + 8 * t;
-        if (row < m) qout[row + j * ldm] = cscale(qc[t], sg);
+        if (row < m) qout[row + j * ldq] = cscale(qc[t], sg);
       }
     }
   }
@@ -714,6 +708,8 @@ __global__ void __launch_bounds__(512) k_jacobi(DqaDev d, int l, int mu, int p_s
       cplx myg = cmk(0.0, 0.0);
       int myp = 0, myq = 0;
       bool myact = false;
+      double mya = 0.0, myb = 0.0;
+      const bool onepass = npass == 1;  // then every lane of a group keeps the pair's data: no broadcasts needed
       cplx vp[RS > 0 ? RS : 1], vq[RS > 0 ? RS : 1];
       for (int pass = 0; pass < npass; ++pass) {
         const int u = pass * 4 + grp, pr = warp * ppw + u;
@@ -724,6 +720,11 @@ __global__ void __launch_bounds__(512) k_jacobi(DqaDev d, int l, int mu, int p_s
           act = q < k;  // padded dummy column
         }
         cplx g = cmk(0.0, 0.0);
+        double a0 = 0.0, b0 = 0.0;
+        if (act) {  // cached squared norms, read before the warp-wide reduction (they are rewritten in phase 2)
+          a0 = nrm2[p];
+          b0 = nrm2[q];
+        }
         if (RS > 0) {
           const cplx* xp = L + p * ldl;
           const cplx* xq = L + q * ldl;
@@ -746,11 +747,13 @@ __global__ void __launch_bounds__(512) k_jacobi(DqaDev d, int l, int mu, int p_s
         g.y += __shfl_xor_sync(DQA_FULL, g.y, 2);
         g.x += __shfl_xor_sync(DQA_FULL, g.x, 1);
         g.y += __shfl_xor_sync(DQA_FULL, g.y, 1);
-        if (li == pass) {
+        if (li == pass || onepass) {
           myg = g;
           myact = act;
+          mya = a0;
+          myb = b0;
         }
-        if (li == pass || RS > 0) {
+        if (li == pass || RS > 0 || onepass) {
           myp = p;
           myq = q;
         }
@@ -760,7 +763,7 @@ __global__ void __launch_bounds__(512) k_jacobi(DqaDev d, int l, int mu, int p_s
       cplx rsph = cmk(0.0, 0.0), rcph = cmk(1.0, 0.0);
       int rot = 0;
       if (myact) {
-        const double a = nrm2[myp], b = nrm2[myq];
+        const double a = mya, b = myb;
         const double ag2 = cabs2(myg);
         if (ag2 > tol2 * a * b && ag2 > 0.0) {
           const double rinv = rsqrt(ag2);
@@ -781,22 +784,32 @@ __global__ void __launch_bounds__(512) k_jacobi(DqaDev d, int l, int mu, int p_s
           rsph = cscale(ph, rsn);
           rcph = cscale(ph, rc);
           rot = 1;
-          const double na = a - tt * ag, nb = b + tt * ag;
-          nrm2[myp] = na > 0.0 ? na : 0.0;
-          nrm2[myq] = nb > 0.0 ? nb : 0.0;
-          myrot++;
+          if (!onepass || li == 0) {
+            const double na = a - tt * ag, nb = b + tt * ag;
+            nrm2[myp] = na > 0.0 ? na : 0.0;
+            nrm2[myq] = nb > 0.0 ? nb : 0.0;
+            myrot++;
+          }
         }
       }
       // ---- phase 3: every group applies its pair's rotation, pass by pass ----
       for (int pass = 0; pass < npass; ++pass) {
-        const int src = (lane & ~7) | pass;
-        const int dr = __shfl_sync(DQA_FULL, rot, src);
-        if (!__any_sync(DQA_FULL, dr)) continue;  // warp-uniform
-        const int p = RS > 0 ? myp : __shfl_sync(DQA_FULL, myp, src);
-        const int q = RS > 0 ? myq : __shfl_sync(DQA_FULL, myq, src);
-        const double c = __shfl_sync(DQA_FULL, rc, src), sn = __shfl_sync(DQA_FULL, rsn, src);
-        const cplx sph = cmk(__shfl_sync(DQA_FULL, rsph.x, src), __shfl_sync(DQA_FULL, rsph.y, src));
-        const cplx cph = cmk(__shfl_sync(DQA_FULL, rcph.x, src), __shfl_sync(DQA_FULL, rcph.y, src));
+        int dr = rot, p = myp, q = myq;
+        double c = rc, sn = rsn;
+        cplx sph = rsph, cph = rcph;
+        if (!onepass) {
+          const int src = (lane & ~7) | pass;
+          dr = __shfl_sync(DQA_FULL, rot, src);
+          if (!__any_sync(DQA_FULL, dr)) continue;  // warp-uniform
+          if (RS == 0) {
+            p = __shfl_sync(DQA_FULL, myp, src);
+            q = __shfl_sync(DQA_FULL, myq, src);
+          }
+          c = __shfl_sync(DQA_FULL, rc, src);
+          sn = __shfl_sync(DQA_FULL, rsn, src);
+          sph = cmk(__shfl_sync(DQA_FULL, rsph.x, src), __shfl_sync(DQA_FULL, rsph.y, src));
+          cph = cmk(__shfl_sync(DQA_FULL, rcph.x, src), __shfl_sync(DQA_FULL, rcph.y, src));
+        }
         if (dr) {
           cplx* xp = L + p * ldl;
           cplx* xq = L + q * ldl;

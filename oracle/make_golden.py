@@ -118,6 +118,10 @@ def main():
         # N=21 at the headline bond dimension: a few steps only (the reference needs minutes per step)
         xi = np.load(os.path.join(DATA, "patterns_17-21.1.npy"))
         run_config("c3_n21_chi32", xi, P=100, dt=1.0, chi=32, steps=2, snap_at={1: {0, 16}})
+    if "n12_chi64" in which:
+        # untruncated regime at the largest supported bond: N=12, chi=64 = 2^(N/2)
+        xi = np.load(os.path.join(DATA, "patterns_9-12.npy"))
+        run_config("n12_chi64_untruncated", xi, P=100, dt=0.5, chi=64, steps=5, snap_at={4: {0, 8}})
     if "c3_16" in which:
         xi = np.load(os.path.join(DATA, "patterns_17-21.1.npy"))
         run_config("c3_n21_chi16", xi, P=100, dt=1.0, chi=16, steps=4, snap_at={3: {0, 16}})

@@ -123,8 +123,9 @@ extern "C" int dqa_create(dqa_t** out, const dqa_config* cfg) {
   if (c.N < 2 || c.n_xi < 1 || c.P < 1 || c.chi < 1 || c.batch < 1) return fail(h, DQA_EINVAL, "N>=2, n_xi>=1, P>=1, chi>=1, batch>=1 required");
   if (c.N > 254) return fail(h, DQA_ELIMIT, "N=%d > 254 not supported", c.N);
   if (sector_qr_smem(c.chi) > 227 * 1024 || svd_smem(c.chi) > 227 * 1024 || energy_smem(c.chi) > 227 * 1024 ||
-      lq_smem(c.chi * (c.N + 1), c.chi) > 227 * 1024)
-    return fail(h, DQA_ELIMIT, "chi=%d needs more than 227 KB of shared memory per CTA in this build (max chi 48)", c.chi);
+      false)
+    return fail(h, DQA_ELIMIT, "chi=%d at N=%d needs more than 227 KB of shared memory per CTA in this build (chi <= 64, and chi*(N+1) bounded by the LQ panel)", c.chi, c.N);
+  if (c.chi > 64) return fail(h, DQA_ELIMIT, "chi=%d > 64 not supported", c.chi);
   h->stream = (cudaStream_t)c.stream;
   h->ws = nullptr;
   h->ws_bytes = 0;
@@ -155,6 +156,8 @@ extern "C" int dqa_create(dqa_t** out, const dqa_config* cfg) {
       if (v > qm) qm = v;
     }
     d.qmax = (int)qm;
+    if (lq_smem(d.qmax, c.chi) > 227 * 1024)
+      return fail(h, DQA_ELIMIT, "chi=%d, N=%d: the LQ panel (8 x %d columns) does not fit in shared memory", c.chi, c.N, d.qmax);
   }
   d.kh = d.D / 2 + 1;
   d.max_sweeps = c.max_sweeps;
@@ -191,6 +194,7 @@ extern "C" int dqa_create(dqa_t** out, const dqa_config* cfg) {
   CK(cudaFuncSetAttribute(k_sector_qr<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sector_qr_smem(c.chi)));
   CK(cudaFuncSetAttribute(k_sector_qr<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sector_qr_smem(c.chi)));
   CK(cudaFuncSetAttribute(k_sector_qr<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sector_qr_smem(c.chi)));
+  CK(cudaFuncSetAttribute(k_sector_qr<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sector_qr_smem(c.chi)));
   CK(cudaFuncSetAttribute(k_jacobi<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)svd_smem(c.chi)));
   CK(cudaFuncSetAttribute(k_jacobi<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)svd_smem(c.chi)));
   CK(cudaFuncSetAttribute(k_jacobi<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)svd_smem(c.chi)));
@@ -361,7 +365,8 @@ static int launch_canonize(dqa_t* h, int mu) {
     if (d.chi <= 8) HL(k_sector_qr<2>, grid, block, sm, h->stream, d, n, mu);
     else if (d.chi <= 16) HL(k_sector_qr<4>, grid, block, sm, h->stream, d, n, mu);
     else if (d.chi <= 32) HL(k_sector_qr<8>, grid, block, sm, h->stream, d, n, mu);
-    else HL(k_sector_qr<12>, grid, block, sm, h->stream, d, n, mu);
+    else if (d.chi <= 48) HL(k_sector_qr<12>, grid, block, sm, h->stream, d, n, mu);
+    else HL(k_sector_qr<16>, grid, block, sm, h->stream, d, n, mu);
     prof_b(h);
   }
   CK(cudaGetLastError());

@@ -99,7 +99,7 @@ __global__ void k_init_plus(DqaDev d) {
 // column with no block barrier at all (column j only needs reflectors j..0).
 // shared memory: M (2chi x chi, col-major; column k ends up holding reflector v_k) | tau | beta
 // ---------------------------------------------------------------------------------
-__host__ __device__ inline int sector_qr_maxs(int chi) { return chi <= 8 ? 2 : (chi <= 16 ? 4 : (chi <= 32 ? 8 : 12)); }
+__host__ __device__ inline int sector_qr_maxs(int chi) { return chi <= 8 ? 2 : (chi <= 16 ? 4 : (chi <= 32 ? 8 : (chi <= 48 ? 12 : 16))); }
 __host__ __device__ inline size_t sector_qr_smem(int chi) {  // M has 8*MAXS rows so every register slot has a row
   return sizeof(cplx) * ((size_t)8 * sector_qr_maxs(chi) * chi + chi) + sizeof(double) * chi;
 }
@@ -119,20 +119,32 @@ __device__ __forceinline__ void sqr_publish(cplx (&col)[MAXS], int k, int m, int
     if (row > k && row < m) ss += cabs2(col[t]);
     if (row == k) alpha = col[t];
   }
+  // the three reductions are independent: issue them together (alpha lives in lane k&7 of the group)
+  const int src = (threadIdx.x & 24) | (k & 7);
+  alpha.x = __shfl_sync(DQA_FULL, alpha.x, src);
+  alpha.y = __shfl_sync(DQA_FULL, alpha.y, src);
   ss += __shfl_xor_sync(DQA_FULL, ss, 4);
   ss += __shfl_xor_sync(DQA_FULL, ss, 2);
   ss += __shfl_xor_sync(DQA_FULL, ss, 1);
-  // alpha lives in lane (k & 7) of the group: sum-broadcast (all other lanes hold 0)
-  alpha.x += __shfl_xor_sync(DQA_FULL, alpha.x, 4);
-  alpha.y += __shfl_xor_sync(DQA_FULL, alpha.y, 4);
-  alpha.x += __shfl_xor_sync(DQA_FULL, alpha.x, 2);
-  alpha.y += __shfl_xor_sync(DQA_FULL, alpha.y, 2);
-  alpha.x += __shfl_xor_sync(DQA_FULL, alpha.x, 1);
-  alpha.y += __shfl_xor_sync(DQA_FULL, alpha.y, 1);
   if (j != k) return;
+  // zlarfg without divisions on the critical path: 1/beta = -+rsqrt(|alpha|^2+ss), one reciprocal for 1/(alpha-beta)
   double beta;
   cplx t_, scal;
-  householder_gen(alpha, ss, beta, t_, scal);
+  if (ss == 0.0 && alpha.y == 0.0) {
+    beta = alpha.x;
+    t_ = cmk(0.0, 0.0);
+    scal = cmk(0.0, 0.0);
+  } else {
+    const double s2 = cabs2(alpha) + ss;
+    const double rs = rsqrt(s2);
+    const double nrm = s2 * rs;
+    const double ib = (alpha.x >= 0.0) ? -rs : rs;  // 1/beta
+    beta = (alpha.x >= 0.0) ? -nrm : nrm;
+    t_ = cmk(1.0 - alpha.x * ib, -alpha.y * ib);
+    const double dx = alpha.x - beta;
+    const double inv = 1.0 / fma(dx, dx, alpha.y * alpha.y);
+    scal = cmk(dx * inv, -alpha.y * inv);
+  }
 #pragma unroll
   for (int t = 0; t < MAXS; ++t) {
     const int row = li + 8 * t;
@@ -171,6 +183,7 @@ __device__ __forceinline__ void sqr_apply(cplx (&col)[MAXS], const cplx* vk, cpl
   switch (t0) {  // fall through on purpose
     SQR_DOT(0) SQR_DOT(1) SQR_DOT(2) SQR_DOT(3) SQR_DOT(4) SQR_DOT(5)
     SQR_DOT(6) SQR_DOT(7) SQR_DOT(8) SQR_DOT(9) SQR_DOT(10) SQR_DOT(11)
+    SQR_DOT(12) SQR_DOT(13) SQR_DOT(14) SQR_DOT(15)
     default: break;
   }
   w.x += __shfl_xor_sync(DQA_FULL, w.x, 4);
@@ -184,6 +197,7 @@ __device__ __forceinline__ void sqr_apply(cplx (&col)[MAXS], const cplx* vk, cpl
     switch (t0) {  // fall through on purpose
       SQR_UPD(0) SQR_UPD(1) SQR_UPD(2) SQR_UPD(3) SQR_UPD(4) SQR_UPD(5)
       SQR_UPD(6) SQR_UPD(7) SQR_UPD(8) SQR_UPD(9) SQR_UPD(10) SQR_UPD(11)
+      SQR_UPD(12) SQR_UPD(13) SQR_UPD(14) SQR_UPD(15)
       default: break;
     }
   }
@@ -631,8 +645,11 @@ __global__ void __launch_bounds__(1024) k_lq(DqaDev d, int l) {
 // Squared column norms are cached (exact recomputation every sweep).
 // shared: L (2chi x 2chi col-major, ld = mr) | nrm2/sig, ssorted (2chi doubles) | order | sh_i
 // ---------------------------------------------------------------------------------
+// L lives in shared memory while (2chi)^2 complex fit next to two more CTAs' worth of headroom; beyond
+// that (chi > 56) the kernel iterates on the L2-resident copy in `lbuf` (same code, generic pointers).
+__host__ __device__ inline bool svd_l_in_smem(int chi) { return sizeof(cplx) * (size_t)(2 * chi) * (2 * chi) <= 200 * 1024; }
 __host__ __device__ inline size_t svd_smem(int chi) {
-  return sizeof(cplx) * (size_t)(2 * chi) * (2 * chi) + sizeof(double) * (4 * chi + 8) + sizeof(int) * (2 * chi + 8);
+  return (svd_l_in_smem(chi) ? sizeof(cplx) * (size_t)(2 * chi) * (2 * chi) : 0) + sizeof(double) * (4 * chi + 8) + sizeof(int) * (2 * chi + 8);
 }
 
 __device__ __forceinline__ void rr_pair(int n, int round, int idx, int& p, int& q) {
@@ -660,8 +677,10 @@ __global__ void __launch_bounds__(512) k_jacobi(DqaDev d, int l, int mu, int p_s
   const int inst = blockIdx.x, tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarp = nt >> 5;
   const int chi = d.chi;
   const size_t rsz = (size_t)chi * chi;
-  cplx* L = (cplx*)smraw;
-  double* sig = (double*)(L + (size_t)(2 * chi) * (2 * chi));
+  const bool lsm = svd_l_in_smem(chi);
+  cplx* lglob = d.lbuf + (size_t)inst * (size_t)(2 * chi) * (2 * chi);
+  cplx* L = lsm ? (cplx*)smraw : lglob;
+  double* sig = (double*)(smraw + (lsm ? sizeof(cplx) * (size_t)(2 * chi) * (2 * chi) : 0));
   double* ssorted = sig + 2 * chi;
   int* order = (int*)(ssorted + 2 * chi + 8);
   int* sh_i = order + 2 * chi;  // [0]=rotation count, [1]=n_chi
@@ -670,11 +689,12 @@ __global__ void __launch_bounds__(512) k_jacobi(DqaDev d, int l, int mu, int p_s
   const int* qd1 = d.qdim + ((size_t)inst * (d.N + 1) + (l + 1)) * d.smax;
   const int Q = qdim_prefix(qd1, d.N - l);
   const int k = mr < Q ? mr : Q;
-  const int ldl = mr;
-  const cplx* lin = d.lbuf + (size_t)inst * (size_t)(2 * chi) * (2 * chi);
-  for (int i = tid; i < mr * k; i += nt) {
-    const int r = i % mr, c = i / mr;
-    L[r + c * ldl] = lin[r + c * (2 * chi)];
+  const int ldl = lsm ? mr : 2 * chi;
+  if (lsm) {
+    for (int i = tid; i < mr * k; i += nt) {
+      const int r = i % mr, c = i / mr;
+      L[r + c * ldl] = lglob[r + c * (2 * chi)];
+    }
   }
   __syncthreads();
 
@@ -940,7 +960,10 @@ __global__ void k_mixer(DqaDev d, double cb, double sb) {
 // n_phys_sites < N_sites supports the ancilla variant (lib/dQA_loss.py:28-46): trailing
 // sites carry the identity.
 // ---------------------------------------------------------------------------------
-__host__ __device__ inline size_t energy_smem(int chi) { return sizeof(cplx) * (size_t)4 * chi * chi; }
+// E, E2 and one W buffer per spin value (4 chi^2) while that fits; beyond chi = 56 the two spin values
+// share one W buffer and are processed one after the other (3 chi^2).
+__host__ __device__ inline bool energy_two_w(int chi) { return sizeof(cplx) * (size_t)4 * chi * chi <= 200 * 1024; }
+__host__ __device__ inline size_t energy_smem(int chi) { return sizeof(cplx) * (size_t)(energy_two_w(chi) ? 4 : 3) * chi * chi; }
 
 // where the site tensors of one MPS live: the plan's padded layout or a packed external MPS
 struct EnergyView {
@@ -959,10 +982,11 @@ __device__ __forceinline__ cplx energy_sweep(const EnergyView& v, const uint8_t*
   const int lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5, g = lane >> 2, t = lane & 3;
   const int chi = v.chi;
   const size_t rsz = (size_t)chi * chi;
+  const bool two_w = energy_two_w(chi);
   cplx* E = smem;
   cplx* E2 = E + rsz;
   cplx* W0 = E2 + rsz;
-  cplx* W1 = W0 + rsz;
+  cplx* W1 = W0 + rsz;  // only touched when two_w
   if (tid == 0) E[0] = cmk(1.0, 0.0);
   __syncthreads();
   for (int i = 0; i < v.n_sites; ++i) {
@@ -970,44 +994,50 @@ __device__ __forceinline__ cplx energy_sweep(const EnergyView& v, const uint8_t*
     const cplx* a = v.off ? v.base + v.off[i] : v.base + (size_t)i * (2 * rsz);
     const int lda = v.off ? br : chi;
     const int tr = (bl + 7) >> 3, tc = (br + 7) >> 3;
-    // phase 1 (DMMA): W_s[c,b] = sum_a E[a,c] A[a,s,b], both s
-    for (int tile = warp; tile < 2 * tr * tc; tile += nwarp) {
-      const int s = tile / (tr * tc), rem = tile % (tr * tc), c0 = (rem / tc) * 8, b0 = (rem % tc) * 8;
-      ZTile acc = ztile_zero();
-      warp_zgemm_8x8(
-          acc, bl,
-          [&](int row, int kk) { return (c0 + row < bl && kk < bl) ? E[kk * bl + c0 + row] : cmk(0.0, 0.0); },
-          [&](int kk, int col) { return (kk < bl && b0 + col < br) ? a[((size_t)kk * 2 + s) * lda + b0 + col] : cmk(0.0, 0.0); });
-      cplx* W = s ? W1 : W0;
-      const int c = c0 + g, b = b0 + 2 * t;
-      if (c < bl) {
-        if (b < br) W[c * br + b] = cmk(acc.r0, acc.i0);
-        if (b + 1 < br) W[c * br + b + 1] = cmk(acc.r1, acc.i1);
-      }
-    }
-    __syncthreads();
-    // phase 2 (DMMA): E2[b,dd] = sum_s ph_s sum_c W_s[c,b] conj(A[c,s,dd])
-    for (int tile = warp; tile < tc * tc; tile += nwarp) {
-      const int b0 = (tile / tc) * 8, d0 = (tile % tc) * 8;
-      cplx out0 = cmk(0.0, 0.0), out1 = cmk(0.0, 0.0);
-      for (int s = 0; s < 2; ++s) {
-        const cplx* W = s ? W1 : W0;
+    // two_w: phase 1 computes W_0 and W_1 together, phase 2 combines them (2 barriers per site);
+    // otherwise the spin values take turns in the single W buffer (4 barriers per site)
+    const int ngrp = two_w ? 1 : 2;
+    for (int grp_s = 0; grp_s < ngrp; ++grp_s) {
+      const int s_lo = two_w ? 0 : grp_s, s_hi = two_w ? 2 : grp_s + 1;
+      // phase 1 (DMMA): W_s[c,b] = sum_a E[a,c] A[a,s,b]
+      for (int tile = warp; tile < (s_hi - s_lo) * tr * tc; tile += nwarp) {
+        const int s = s_lo + tile / (tr * tc), rem = tile % (tr * tc), c0 = (rem / tc) * 8, b0 = (rem % tc) * 8;
         ZTile acc = ztile_zero();
         warp_zgemm_8x8(
             acc, bl,
-            [&](int row, int kk) { return (b0 + row < br && kk < bl) ? W[kk * br + b0 + row] : cmk(0.0, 0.0); },
-            [&](int kk, int col) { return (kk < bl && d0 + col < br) ? cconj(a[((size_t)kk * 2 + s) * lda + d0 + col]) : cmk(0.0, 0.0); });
-        const cplx ph = (i < v.n_phys && (hb[i] ^ s)) ? wk : cmk(1.0, 0.0);
-        out0 = cfma(ph, cmk(acc.r0, acc.i0), out0);
-        out1 = cfma(ph, cmk(acc.r1, acc.i1), out1);
+            [&](int row, int kk) { return (c0 + row < bl && kk < bl) ? E[kk * bl + c0 + row] : cmk(0.0, 0.0); },
+            [&](int kk, int col) { return (kk < bl && b0 + col < br) ? a[((size_t)kk * 2 + s) * lda + b0 + col] : cmk(0.0, 0.0); });
+        cplx* W = (two_w && s) ? W1 : W0;
+        const int c = c0 + g, b = b0 + 2 * t;
+        if (c < bl) {
+          if (b < br) W[c * br + b] = cmk(acc.r0, acc.i0);
+          if (b + 1 < br) W[c * br + b + 1] = cmk(acc.r1, acc.i1);
+        }
       }
-      const int b = b0 + g, dd = d0 + 2 * t;
-      if (b < br) {
-        if (dd < br) E2[b * br + dd] = out0;
-        if (dd + 1 < br) E2[b * br + dd + 1] = out1;
+      __syncthreads();
+      // phase 2 (DMMA): E2[b,dd] (+)= sum_s ph_s sum_c W_s[c,b] conj(A[c,s,dd])
+      for (int tile = warp; tile < tc * tc; tile += nwarp) {
+        const int b0 = (tile / tc) * 8, d0 = (tile % tc) * 8;
+        cplx out0 = cmk(0.0, 0.0), out1 = cmk(0.0, 0.0);
+        for (int s = s_lo; s < s_hi; ++s) {
+          const cplx* W = (two_w && s) ? W1 : W0;
+          ZTile acc = ztile_zero();
+          warp_zgemm_8x8(
+              acc, bl,
+              [&](int row, int kk) { return (b0 + row < br && kk < bl) ? W[kk * br + b0 + row] : cmk(0.0, 0.0); },
+              [&](int kk, int col) { return (kk < bl && d0 + col < br) ? cconj(a[((size_t)kk * 2 + s) * lda + d0 + col]) : cmk(0.0, 0.0); });
+          const cplx ph = (i < v.n_phys && (hb[i] ^ s)) ? wk : cmk(1.0, 0.0);
+          out0 = cfma(ph, cmk(acc.r0, acc.i0), out0);
+          out1 = cfma(ph, cmk(acc.r1, acc.i1), out1);
+        }
+        const int b = b0 + g, dd = d0 + 2 * t;
+        if (b < br) {
+          if (dd < br) E2[b * br + dd] = (grp_s == 0) ? out0 : cadd(E2[b * br + dd], out0);
+          if (dd + 1 < br) E2[b * br + dd + 1] = (grp_s == 0) ? out1 : cadd(E2[b * br + dd + 1], out1);
+        }
       }
+      __syncthreads();
     }
-    __syncthreads();
     cplx* t2 = E;
     E = E2;
     E2 = t2;

@@ -255,7 +255,7 @@ extern "C" int dqa_op_energy(dqa_ops_t* h, int n_sites, int n_phys, int n_xi, co
     chi = std::max(chi, (int)std::max(bonds[i], bonds[i + 1]));
   }
   if (bonds[0] != 1 || bonds[n_sites] != 1) return ofail(h, DQA_EINVAL, "boundary bonds must be 1");
-  if (energy_smem(chi) > 200 * 1024) return ofail(h, DQA_ELIMIT, "bond %d too large for the energy kernel (max 56)", chi);
+  if (energy_smem(chi) > 200 * 1024) return ofail(h, DQA_ELIMIT, "bond %d too large for the energy kernel (max 64)", chi);
   std::vector<uint8_t> hb((size_t)n_xi * n_phys);
   for (size_t i = 0; i < hb.size(); ++i) {
     if (xi[i] != 1 && xi[i] != -1) return ofail(h, DQA_EINVAL, "pattern entry %zu is not +-1", i);

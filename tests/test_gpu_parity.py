@@ -23,7 +23,7 @@ def factory():
     return make
 
 
-@pytest.mark.parametrize("name", ["n7_chi4", "c1_n12_chi10", "c2_n21_chi10", "n15_chi10"])
+@pytest.mark.parametrize("name", ["n7_chi4", "c1_n12_chi10", "c2_n21_chi10", "n15_chi10", "c3_n21_chi32"])
 def test_p0_index_tensors_bit_exact(factory, name):
     ps.check_index_tensors(factory, name)
 
@@ -53,9 +53,41 @@ def test_p4_eps0_notebook_value(factory):
     assert abs(pl.eps_trace()[0, 0].real - 0.2930447289172962) < 1e-14
 
 
-@pytest.mark.parametrize("name", ["n7_chi4", "n7_chi8_untruncated", "c1_n12_chi10", "c2_n21_chi10", "n15_chi10"])
+@pytest.mark.parametrize("name", ["n7_chi4", "n7_chi8_untruncated", "c1_n12_chi10", "c2_n21_chi10", "n15_chi10",
+                                  "c3_n21_chi32", "n12_chi64_untruncated"])
 def test_p1_teacher_forced_substeps(factory, name):
+    """includes the headline bond dimension (N=21, chi=32) and the largest supported one (chi=64)"""
     ps.check_teacher_forced(factory, name)
+
+
+def test_p3_untruncated_chi64(factory):
+    """N=12, chi=64=2^(N/2): nothing is truncated by chi, so the run must follow the reference to roundoff and
+    the exact state-vector dQA up to the 1e-10 relative-weight cutoff."""
+    d, _ = ps.check_free_run(factory, "n12_chi64_untruncated", steps=5, tol=1e-10)
+    g = golden("n12_chi64_untruncated")
+    sv = O.statevector_dqa(g["xi"], int(g["P"]), float(g["dt"]), steps=5)
+    pl = ps.make(factory, g)
+    pl.reset_plus()
+    pl.step(5)
+    assert np.abs(pl.eps_trace()[0, :6].real - sv).max() < 1e-6
+    assert d.max() < 1e-11
+
+
+def test_p3_cutoff_zero_matches_exact_statevector():
+    """With the cutoff plan field at 0 and chi large enough nothing is discarded: the MPS run IS the exact
+    Trotterised dQA (to roundoff), whole trajectory."""
+    from perceptron_dqa_b200._lib import Plan
+
+    g = golden("n7_chi8_untruncated")
+    xi = g["xi"]
+    pl = Plan(7, xi.shape[0], int(g["P"]), float(g["dt"]), 8, batch=1, cutoff=-1.0)
+    pl.set_patterns(xi[None])
+    pl.set_fourier(g["Uk_FT"], g["fxft"])
+    pl.reset_plus()
+    pl.step(int(g["P"]))
+    sv = O.statevector_dqa(xi, int(g["P"]), float(g["dt"]))
+    assert np.abs(pl.eps_trace()[0].real - sv).max() < 1e-10
+    assert not pl.status().any()
 
 
 @pytest.mark.parametrize("name", ["n7_chi4", "c1_n12_chi10", "c2_n21_chi10"])
@@ -136,4 +168,4 @@ def test_errors_are_reported():
     with pytest.raises(DqaError):
         pl.set_patterns(np.zeros((1, 5, 7), dtype=np.int8))  # not +-1
     with pytest.raises(DqaError):
-        Plan(7, 5, 4, 1.0, 400)  # chi beyond the shared-memory limit
+        Plan(7, 5, 4, 1.0, 65)  # chi beyond what the kernels support

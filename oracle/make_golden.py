@@ -122,6 +122,11 @@ def main():
         # untruncated regime at the largest supported bond: N=12, chi=64 = 2^(N/2)
         xi = np.load(os.path.join(DATA, "patterns_9-12.npy"))
         run_config("n12_chi64_untruncated", xi, P=100, dt=0.5, chi=64, steps=5, snap_at={4: {0, 8}})
+    if "n32" in which:
+        # scaled-down analogue of the N=64 instance: synthetic iid +-1 patterns, default_rng(64)
+        rng = np.random.default_rng(64)
+        xi = (2 * rng.integers(0, 2, size=(4, 32)) - 1).astype(np.int8)
+        run_config("n32_chi8_synthetic", xi, P=50, dt=1.0, chi=8, steps=3, snap_at={2: {0, 3}})
     if "c3_16" in which:
         xi = np.load(os.path.join(DATA, "patterns_17-21.1.npy"))
         run_config("c3_n21_chi16", xi, P=100, dt=1.0, chi=16, steps=4, snap_at={3: {0, 16}})

@@ -156,8 +156,9 @@ extern "C" int dqa_create(dqa_t** out, const dqa_config* cfg) {
       if (v > qm) qm = v;
     }
     d.qmax = (int)qm;
-    if (lq_smem(d.qmax, c.chi) > 227 * 1024)
-      return fail(h, DQA_ELIMIT, "chi=%d, N=%d: the LQ panel (8 x %d columns) does not fit in shared memory", c.chi, c.N, d.qmax);
+    d.lq_pb = lq_pick_pb(d.qmax, c.chi);
+    if (lq_smem(d.qmax, c.chi, d.lq_pb) > 227 * 1024)
+      return fail(h, DQA_ELIMIT, "chi=%d, N=%d: one LQ panel row (%d columns) does not fit in shared memory", c.chi, c.N, d.qmax);
   }
   d.kh = d.D / 2 + 1;
   d.max_sweeps = c.max_sweeps;
@@ -198,7 +199,7 @@ extern "C" int dqa_create(dqa_t** out, const dqa_config* cfg) {
   CK(cudaFuncSetAttribute(k_jacobi<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)svd_smem(c.chi)));
   CK(cudaFuncSetAttribute(k_jacobi<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)svd_smem(c.chi)));
   CK(cudaFuncSetAttribute(k_jacobi<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)svd_smem(c.chi)));
-  CK(cudaFuncSetAttribute(k_lq, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lq_smem(h->dev.qmax, c.chi)));
+  CK(cudaFuncSetAttribute(k_lq, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lq_smem(h->dev.qmax, c.chi, h->dev.lq_pb)));
   CK(cudaFuncSetAttribute(k_energy, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)energy_smem(c.chi)));
   CK(cudaFuncSetAttribute(k_theta, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(cplx) * c.chi * c.chi)));
   return DQA_OK;
@@ -385,7 +386,7 @@ static int launch_truncate(dqa_t* h, int p, int mu) {
       prof_b(h);
     }
     prof_a(h, 2);
-    HL(k_lq, dim3(d.batch), dim3(h->t_lq), lq_smem(d.qmax, d.chi), h->stream, d, l);
+    HL(k_lq, dim3(d.batch), dim3(h->t_lq), lq_smem(d.qmax, d.chi, d.lq_pb), h->stream, d, l);
     prof_b(h);
     prof_a(h, 5);
     {

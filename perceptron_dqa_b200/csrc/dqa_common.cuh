@@ -126,6 +126,7 @@ struct DqaDev {
   int N, D, n_xi, chi, batch, P;
   int smax;        // N+1 sectors at most per bond
   int ld_theta;    // row stride of Theta (>= chi*(N+1))
+  int lq_pb;       // rows per LQ panel (8, or fewer when a panel of qmax columns would not fit in shared memory)
   int qmax;        // bound on the live columns of Theta: max_n min(chi,2^n,2^(N-n)) * (N-n+1)
   int nsec_total;  // number of (site, sector) Q blocks per instance
   int kh;          // D/2+1: independent Fourier modes of the energy sweep

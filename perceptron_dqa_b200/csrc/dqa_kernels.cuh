@@ -443,8 +443,14 @@ __global__ void __launch_bounds__(256) k_theta(DqaDev d, int l, int mu) {
 #define LQ_MAXW 16  // partial-W tiles kept in shared memory (>= row tiles, <= warps per CTA)
 __host__ __device__ inline int lq_npad(int ncols) { return ((ncols + 7) & ~7) + 4; }
 // qmax = largest number of Theta columns any cut can have (host-computed bound), chi sets the row tiles
-__host__ __device__ inline size_t lq_smem(int qmax, int chi) {
-  return sizeof(cplx) * ((size_t)LQ_PB * lq_npad(qmax) + 2 * LQ_PB * LQ_PB + LQ_PB + (size_t)LQ_MAXW * 64 + (size_t)((2 * chi + 7) / 8) * 64);
+__host__ __device__ inline size_t lq_smem(int qmax, int chi, int pb) {
+  return sizeof(cplx) * ((size_t)pb * lq_npad(qmax) + 2 * LQ_PB * LQ_PB + LQ_PB + (size_t)LQ_MAXW * 64 + (size_t)((2 * chi + 7) / 8) * 64);
+}
+// panel height: 8 rows unless the panel (pb x qmax) would not leave room for two CTAs per SM / fit at all
+__host__ __device__ inline int lq_pick_pb(int qmax, int chi) {
+  int pb = LQ_PB;
+  while (pb > 1 && lq_smem(qmax, chi, pb) > 180 * 1024) pb >>= 1;
+  return pb;
 }
 
 __global__ void __launch_bounds__(1024) k_lq(DqaDev d, int l) {
@@ -452,7 +458,8 @@ __global__ void __launch_bounds__(1024) k_lq(DqaDev d, int l) {
   const int inst = blockIdx.x, tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarp = nt >> 5;
   const int chi = d.chi, ld = d.ld_theta, npad = lq_npad(d.qmax);
   cplx* Vp = (cplx*)smraw;
-  cplx* Tm = Vp + (size_t)LQ_PB * npad;
+  const int pbmax = d.lq_pb;
+  cplx* Tm = Vp + (size_t)pbmax * npad;
   cplx* Sg = Tm + LQ_PB * LQ_PB;
   cplx* taus = Sg + LQ_PB * LQ_PB;
   cplx* Wp = taus + LQ_PB;            // LQ_MAXW partial 8x8 tiles
@@ -471,8 +478,8 @@ __global__ void __launch_bounds__(1024) k_lq(DqaDev d, int l) {
   cplx* lout = d.lbuf + (size_t)inst * (size_t)(2 * chi) * (2 * chi);
   const int ldl = 2 * chi;
 
-  for (int p0 = 0; p0 < k; p0 += LQ_PB) {
-    const int pb = (k - p0) < LQ_PB ? (k - p0) : LQ_PB;
+  for (int p0 = 0; p0 < k; p0 += pbmax) {
+    const int pb = (k - p0) < pbmax ? (k - p0) : pbmax;
     const int n = Q - p0;  // panel columns p0..Q-1
     const cplx* src = (p0 == 0) ? th : wk;
     for (int i = tid; i < pb * n; i += nt) {

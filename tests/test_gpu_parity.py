@@ -54,7 +54,7 @@ def test_p4_eps0_notebook_value(factory):
 
 
 @pytest.mark.parametrize("name", ["n7_chi4", "n7_chi8_untruncated", "c1_n12_chi10", "c2_n21_chi10", "n15_chi10",
-                                  "c3_n21_chi32", "n12_chi64_untruncated"])
+                                  "c3_n21_chi32", "n12_chi64_untruncated", "n32_chi8_synthetic"])
 def test_p1_teacher_forced_substeps(factory, name):
     """includes the headline bond dimension (N=21, chi=32) and the largest supported one (chi=64)"""
     ps.check_teacher_forced(factory, name)
@@ -71,6 +71,48 @@ def test_p3_untruncated_chi64(factory):
     pl.step(5)
     assert np.abs(pl.eps_trace()[0, :6].real - sv).max() < 1e-6
     assert d.max() < 1e-11
+
+
+def test_n64_instance_scaled_down_checks():
+    """C5 (N=64, N_xi=51, chi=64) has no CPU oracle (days per step).  What can be checked: the
+    integer tables and eps(0) at full size, and teacher-forced sub-steps at N=64 with chi=8 against the numpy
+    statement of the same algorithm (oracle/sector_model.py, itself pinned to the reference at N<=32)."""
+    import sector_model as S
+    from perceptron_dqa_b200._lib import Plan
+
+    rng = np.random.default_rng(64)
+    xi = (2 * rng.integers(0, 2, size=(51, 64)) - 1).astype(np.int8)
+    P, dt = 1000, 1.0
+    uk, fx = O.fourier_tables(64, P, dt)
+    big = Plan(64, 51, P, dt, 64, batch=1)
+    big.set_patterns(xi[None])
+    big.set_fourier(uk, fx)
+    big.reset_plus()
+    assert abs(big.eps_trace()[0, 0].real - 0.3166677775716445) < 1e-13
+    big.pp = P // 2
+    big.apply_pattern(P // 2, 0)   # one full-size sub-step runs and keeps the norm
+    st = big.get_mps(0)
+    assert abs(O.mps_norm2(st) - 1) < 1e-12 and not big.status().any()
+    del big
+    pl = Plan(64, 51, P, dt, 8, batch=1)
+    pl.set_patterns(xi[None])
+    pl.set_fourier(uk, fx)
+    pl.reset_plus()
+    hbit, _, _ = O.hamming_tables(xi)
+    fxv = O.f_perceptron(np.arange(65), 64)
+    psi = O.plus_state(64)
+    for p, mu in ((499, 0), (499, 1), (500, 7), (500, 50)):
+        u = np.exp(-1j * (p + 1) / P * dt * fxv)
+        nbit = np.stack([hbit[mu] ^ 0, hbit[mu] ^ 1], axis=1)
+        want = S.apply_pattern_sector(psi, u, nbit, 8)
+        pl.set_mps(psi, 0)
+        pl.apply_pattern(p, mu)
+        got = pl.get_mps(0)
+        assert [t.shape for t in got] == [t.shape for t in want]
+        assert abs(O.fidelity_defect(got, want)) < 1e-12
+        psi = S.mixer(want, 0.3)
+    pl.set_mps(psi, 0)
+    assert abs(pl.energy()[0] - O.compute_loss_fast(psi, xi, fx)) < 1e-11
 
 
 def test_p3_cutoff_zero_matches_exact_statevector():

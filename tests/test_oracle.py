@@ -10,7 +10,7 @@ import sector_model as S
 from helpers import compare_states, golden, snapshots
 
 CONFIGS = ["n7_chi4", "n7_chi8_untruncated", "c1_n12_chi10", "n15_chi10", "c2_n21_chi10"]
-BIG = ["c3_n21_chi32", "n12_chi64_untruncated"]  # tables only on the CPU (a reference sub-step takes ~10 s here)
+BIG = ["c3_n21_chi32", "n12_chi64_untruncated", "n32_chi8_synthetic"]  # tables only on the CPU (a reference sub-step takes ~10 s here)
 
 
 @pytest.mark.parametrize("name", CONFIGS + BIG)
@@ -63,7 +63,7 @@ def test_oracle_substeps_teacher_forced(name):
         compare_states(got, post, g["xi"], g["fxft"])
 
 
-@pytest.mark.parametrize("name", ["n7_chi4", "c1_n12_chi10", "c2_n21_chi10"])
+@pytest.mark.parametrize("name", ["n7_chi4", "c1_n12_chi10", "c2_n21_chi10", "n32_chi8_synthetic"])
 def test_sector_model_equals_reference_substep(name):
     """The product's algorithm (counter-bond sectors + Householder LQ + one-sided Jacobi),
     stated in numpy, reproduces the reference's sub-step on gauge-invariant quantities."""

@@ -164,6 +164,11 @@ int dqa_op_normalize(dqa_ops_t* ctx, double* x, long n);
 int dqa_op_energy(dqa_ops_t* ctx, int n_sites, int n_phys, int n_xi, const int32_t* bonds, const double* mps, const int8_t* xi,
                   const double* fxft, double* eps);
 
+/* Exact (untruncated) state-vector dQA on the GPU -- the gauge-free validator of SURVEY 8f-3, same conventions as the MPS
+ * path (site 0 = most significant bit, s=0 <-> sigma=+1): nsteps Trotter steps from |+>^N, eps[0..nsteps].  Scratch: 16*2^N B.
+ * ms (optional, 3 doubles): device milliseconds in the diagonal-phase, mixer and energy kernels (all HBM-streaming). */
+int dqa_sv_run(dqa_ops_t* ctx, int N, int n_xi, const int8_t* xi, int P, double dt, int nsteps, double* eps, double* ms);
+
 #ifdef __cplusplus
 }
 #endif

@@ -84,6 +84,7 @@ _SIGS = {
     "dqa_op_compress_onesite": ([_P, _P, C.c_int, C.c_int, _P, C.c_int, C.c_int, _P, _P, C.POINTER(C.c_int)], C.c_int),
     "dqa_op_normalize": ([_P, _P, C.c_long], C.c_int),
     "dqa_op_energy": ([_P, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P], C.c_int),
+    "dqa_sv_run": ([_P, C.c_int, C.c_int, _P, C.c_int, C.c_double, C.c_int, _P, _P], C.c_int),
 }
 EXPORTS = tuple(_SIGS)
 
@@ -417,3 +418,13 @@ class Ops:
         assert xi.shape[1] == n_phys and fx.shape[0] == n_phys + 1
         self._ck(self.lib.dqa_op_energy(self._h, len(mps), n_phys, xi.shape[0], _ptr(bonds), _ptr(flat), _ptr(xi), _ptr(fx), _ptr(out)))
         return complex(out[0])
+
+    def statevector_dqa(self, xi, P, dt, steps=None, timings=False):
+        """Exact Trotterised dQA on the device (2^N amplitudes): eps(s) for s = 0..steps/P."""
+        xi = np.ascontiguousarray(xi, dtype=np.int8)
+        n_xi, n = xi.shape
+        steps = P if steps is None else steps
+        eps = np.empty(steps + 1, dtype=np.float64)
+        ms = np.zeros(3, dtype=np.float64)
+        self._ck(self.lib.dqa_sv_run(self._h, n, n_xi, _ptr(xi), int(P), float(dt), int(steps), _ptr(eps), _ptr(ms) if timings else None))
+        return (eps, dict(zip(("phase", "mixer", "energy"), ms.tolist()))) if timings else eps

@@ -163,6 +163,11 @@ extern "C" int dqa_create(dqa_t** out, const dqa_config* cfg) {
   d.kh = d.D / 2 + 1;
   d.max_sweeps = c.max_sweeps;
   d.cutoff = c.cutoff;
+  {
+    const char* env = getenv("DQA_JAC_QUAD");  // relative threshold, default 1e-10; 0 disables the shortcut
+    const double q = env ? atof(env) : 1e-10;
+    d.jac_quad2 = q * q;
+  }
   // block sizes: warps scale with chi; the emulator build keeps them small
 #ifdef DQA_EMUL
   h->t_qr = 32 * ((8 * c.chi + 31) / 32); h->t_theta = 64; h->t_svd = 64; h->t_energy = 64; h->t_lq = 64;

@@ -132,6 +132,7 @@ struct DqaDev {
   int kh;          // D/2+1: independent Fourier modes of the energy sweep
   int max_sweeps;
   double cutoff;
+  double jac_quad2;  // (relative off-diagonal)^2 below which a rotated pair counts as already converged (0: always run the checking sweep)
   cplx* mps;              // [batch][N][chi*2*chi]   site (a,s,c) at (a*2+s)*chi + c
   int* bond;              // [batch][N+1]
   const uint8_t* hbit;    // [batch][n_xi][N]        (1 - xi)/2

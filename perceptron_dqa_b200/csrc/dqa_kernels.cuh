@@ -690,7 +690,7 @@ __global__ void __launch_bounds__(512) k_jacobi(DqaDev d, int l, int mu, int p_s
   double* sig = (double*)(smraw + (lsm ? sizeof(cplx) * (size_t)(2 * chi) * (2 * chi) : 0));
   double* ssorted = sig + 2 * chi;
   int* order = (int*)(ssorted + 2 * chi + 8);
-  int* sh_i = order + 2 * chi;  // [0]=rotation count, [1]=n_chi
+  int* sh_i = order + 2 * chi;  // [0]=rotation count, [1]=n_chi, [2]=some rotated pair was above the quadratic threshold
   int* bond = d.bond + inst * (d.N + 1);
   const int mr = 2 * bond[l];
   const int* qd1 = d.qdim + ((size_t)inst * (d.N + 1) + (l + 1)) * d.smax;
@@ -727,9 +727,12 @@ __global__ void __launch_bounds__(512) k_jacobi(DqaDev d, int l, int mu, int p_s
       a += __shfl_xor_sync(DQA_FULL, a, 1);
       if (li == 0 && j < k) nrm2[j] = a;
     }
-    if (tid == 0) sh_i[0] = 0;
+    if (tid == 0) {
+      sh_i[0] = 0;
+      sh_i[2] = 0;
+    }
     __syncthreads();
-    int myrot = 0;
+    int myrot = 0, mybig = 0;
     for (int round = 0; round < kp - 1; ++round) {
       // ---- phase 1: conj(x_p).x_q for every pair of this warp; lane li==pass of a group keeps it ----
       cplx myg = cmk(0.0, 0.0);
@@ -811,6 +814,7 @@ __global__ void __launch_bounds__(512) k_jacobi(DqaDev d, int l, int mu, int p_s
           rsph = cscale(ph, rsn);
           rcph = cscale(ph, rc);
           rot = 1;
+          if (ag2 > d.jac_quad2 * a * b) mybig = 1;  // an off-diagonal above the quadratic-convergence threshold
           if (!onepass || li == 0) {
             const double na = a - tt * ag, nb = b + tt * ag;
             nrm2[myp] = na > 0.0 ? na : 0.0;
@@ -861,10 +865,14 @@ __global__ void __launch_bounds__(512) k_jacobi(DqaDev d, int l, int mu, int p_s
       __syncthreads();
     }
     if (myrot) atomicAdd(&sh_i[0], myrot);
+    if (mybig) atomicOr(&sh_i[2], 1);
     __syncthreads();
     sweeps++;
     nrot_total += (unsigned long long)sh_i[0];
-    converged = (sh_i[0] == 0);
+    // Converged when a sweep rotated nothing, or when every pair it rotated was already orthogonal to
+    // jac_quad = 1e-10 (relative): cyclic Jacobi converges quadratically, so after such a sweep all
+    // off-diagonals are O(n * 1e-20 / relative gap) << sqrt(m)*eps and the checking sweep is skipped.
+    converged = (sh_i[0] == 0) || (sh_i[2] == 0);
     __syncthreads();
   }
 

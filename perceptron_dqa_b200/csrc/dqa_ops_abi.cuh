@@ -2,6 +2,7 @@
 // Host buffers in, host buffers out; the device scratch is caller-owned (dqa_ops_create).
 #pragma once
 #include "dqa_ops.cuh"
+#include "dqa_sv.cuh"
 
 #include <complex>
 #include <vector>
@@ -290,5 +291,82 @@ extern "C" int dqa_op_energy(dqa_ops_t* h, int n_sites, int n_phys, int n_xi, co
   OCK(cudaGetLastError());
   OCK(cudaMemcpyAsync(eps, dE, sizeof(cplx), cudaMemcpyDeviceToHost, h->stream));
   OCK(cudaStreamSynchronize(h->stream));
+  return DQA_OK;
+}
+
+// Exact state-vector dQA: runs `nsteps` Trotter steps from |+>^N on the device and returns
+// eps(s) for s = 0, 1/P, ..., nsteps/P (nsteps+1 doubles).  Needs 16*2^N bytes of scratch; N <= 40 here.
+// ms_out (optional, 3 doubles): device time spent in the phase / mixer / energy kernels.
+extern "C" int dqa_sv_run(dqa_ops_t* h, int N, int n_xi, const int8_t* xi, int P, double dt, int nsteps, double* eps, double* ms_out) {
+  if (!h || !xi || !eps || N < 2 || N > 40 || n_xi < 1 || n_xi > 64 || P < 1 || nsteps < 0 || nsteps > P) return DQA_EINVAL;
+  const unsigned long long dim = 1ull << N;
+  std::vector<unsigned long long> pat(n_xi, 0ull);
+  for (int mu = 0; mu < n_xi; ++mu)
+    for (int i = 0; i < N; ++i) {
+      const int v = xi[(size_t)mu * N + i];
+      if (v != 1 && v != -1) return ofail(h, DQA_EINVAL, "pattern entry is not +-1");
+      if (v == -1) pat[mu] |= 1ull << (N - 1 - i);
+    }
+  std::vector<double> fx(N + 1);
+  for (int x = 0; x <= N; ++x) {
+    const int m = N - 2 * x;  // f(x) = h(N-2x), h(m) = 0 for m >= 0 else -m/sqrt(N)  (lib/dQA_utils.py:78-95)
+    fx[x] = m >= 0 ? 0.0 : -(double)m / std::sqrt((double)N);
+  }
+#ifdef DQA_EMUL
+  const int nblk = 2;
+#else
+  const int nblk = 148 * 8;
+#endif
+  OCarve cv{h, 0, true};
+  cplx* psi = cv.take<cplx>(dim);
+  unsigned long long* dpat = cv.take<unsigned long long>(n_xi);
+  double* dfx = cv.take<double>(N + 1);
+  double* part = cv.take<double>(nblk);
+  double* dout = cv.take<double>(nsteps + 1);
+  OCARVE_CHECK(cv);
+  OCK(cudaMemcpyAsync(dpat, pat.data(), sizeof(unsigned long long) * n_xi, cudaMemcpyHostToDevice, h->stream));
+  OCK(cudaMemcpyAsync(dfx, fx.data(), sizeof(double) * (N + 1), cudaMemcpyHostToDevice, h->stream));
+  OCK(cudaFuncSetAttribute(k_sv_rx, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+  cudaEvent_t ev[4];
+  float acc_ms[3] = {0.f, 0.f, 0.f};
+  for (auto& e : ev) OCK(cudaEventCreate(&e));
+  DQA_LAUNCH(k_sv_init, dim3(nblk), dim3(256), 0, h->stream, psi, dim, std::pow(2.0, -0.5 * N));
+  DQA_LAUNCH(k_sv_energy, dim3(nblk), dim3(256), 0, h->stream, (const cplx*)psi, dim, (const unsigned long long*)dpat, n_xi, (const double*)dfx, N + 1, part);
+  DQA_LAUNCH(k_sv_energy_final, dim3(1), dim3(256), 0, h->stream, (const double*)part, nblk, 1.0 / N, dout);
+  for (int p = 0; p < nsteps; ++p) {
+    const double sp = (double)(p + 1) / P, gamma = sp * dt, beta = (1.0 - sp) * dt;
+    OCK(cudaEventRecord(ev[0], h->stream));
+    DQA_LAUNCH(k_sv_phase, dim3(nblk), dim3(256), 0, h->stream, psi, dim, (const unsigned long long*)dpat, n_xi, (const double*)dfx, N + 1, gamma);
+    OCK(cudaEventRecord(ev[1], h->stream));
+    // mixer: low 10 bits in one contiguous-tile pass, then groups of up to 7 bits with 32-wide coalesced rows
+    int q0 = 0;
+    while (q0 < N) {
+      const int lowbits = q0 == 0 ? 0 : (q0 < 5 ? q0 : 5);
+      int nq = q0 == 0 ? 10 : 7;
+      if (nq > N - q0) nq = N - q0;
+      const size_t sm = sizeof(cplx) * ((size_t)1 << (nq + lowbits));
+      const unsigned long long ntiles = 1ull << (N - nq - lowbits);
+      DQA_LAUNCH(k_sv_rx, dim3((unsigned)(ntiles < 148 * 16 ? ntiles : 148 * 16)), dim3(256), sm, h->stream, psi, N, q0, nq, lowbits, std::cos(beta), std::sin(beta));
+      q0 += nq;
+    }
+    OCK(cudaEventRecord(ev[2], h->stream));
+    DQA_LAUNCH(k_sv_energy, dim3(nblk), dim3(256), 0, h->stream, (const cplx*)psi, dim, (const unsigned long long*)dpat, n_xi, (const double*)dfx, N + 1, part);
+    DQA_LAUNCH(k_sv_energy_final, dim3(1), dim3(256), 0, h->stream, (const double*)part, nblk, 1.0 / N, dout + p + 1);
+    OCK(cudaEventRecord(ev[3], h->stream));
+    if (ms_out) {
+      OCK(cudaEventSynchronize(ev[3]));
+      for (int j = 0; j < 3; ++j) {
+        float t = 0.f;
+        OCK(cudaEventElapsedTime(&t, ev[j], ev[j + 1]));
+        acc_ms[j] += t;
+      }
+    }
+  }
+  OCK(cudaGetLastError());
+  OCK(cudaMemcpyAsync(eps, dout, sizeof(double) * (nsteps + 1), cudaMemcpyDeviceToHost, h->stream));
+  OCK(cudaStreamSynchronize(h->stream));
+  for (auto& e : ev) cudaEventDestroy(e);
+  if (ms_out)
+    for (int j = 0; j < 3; ++j) ms_out[j] = acc_ms[j];
   return DQA_OK;
 }

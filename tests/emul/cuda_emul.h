@@ -260,6 +260,7 @@ static inline int atomicMax(int* p, int v) { int o = *p; if (v > o) *p = v; retu
 static inline void sincospi(double x, double* s, double* c) { *s = std::sin(M_PI * x); *c = std::cos(M_PI * x); }
 static inline double rsqrt(double x) { return 1.0 / std::sqrt(x); }
 static inline long long clock64() { return 0; }
+static inline int __popcll(unsigned long long x) { return __builtin_popcountll(x); }
 static inline void __threadfence() {}
 static inline void __threadfence_block() {}
 static inline double __ddiv_rn(double a, double b) { return a / b; }

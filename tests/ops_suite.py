@@ -137,3 +137,12 @@ def check_energy_ext(T, ops):
     want = O.compute_loss(ext, xi, fx, n_ancilla=3)
     got = ops.energy(ext, xi, fx, 3)
     assert abs(got - want) < 1e-12 * max(1.0, abs(want))
+
+
+def check_statevector(ops):
+    """GPU/emulated state-vector dQA against the numpy state-vector oracle."""
+    g = golden("n7_chi8_untruncated")
+    got = ops.statevector_dqa(g["xi"], int(g["P"]), float(g["dt"]))
+    want = O.statevector_dqa(g["xi"], int(g["P"]), float(g["dt"]))
+    assert np.abs(got - want).max() < 1e-13
+    assert np.abs(got - g["eps"].real).max() < 1e-6  # the MPS reference run, up to its 1e-10 cutoff

@@ -87,3 +87,4 @@ def test_ops_dense_substep_and_energy(tenn_emul):
     T, o = tenn_emul
     os_.check_dense_substep_equals_reference(T)
     os_.check_energy_ext(T, o)
+    os_.check_statevector(o)

@@ -74,3 +74,32 @@ def test_dense_path_at_reference_sizes(T):
     psi = T.compress_svd_normalized(T.right_canonize(psi, 1), 10)
     assert [t.shape for t in psi] == [t.shape for t in post]
     assert abs(O.fidelity_defect(psi, post)) < 1e-11
+
+
+def test_statevector_validator(T):
+    """exact Trotterised dQA on the device (2^N amplitudes) vs the numpy state vector (N=7, N=12) and
+    as the yardstick of the MPS truncation error at N=21."""
+    from perceptron_dqa_b200._lib import Plan
+
+    os_.check_statevector(T.ops())
+    g = golden("c1_n12_chi10")
+    got = T.ops().statevector_dqa(g["xi"], 100, 0.5, steps=30)
+    assert np.abs(got - O.statevector_dqa(g["xi"], 100, 0.5, steps=30)).max() < 1e-12
+    g = golden("c2_n21_chi10")
+    steps = 4
+    exact, ms = T.ops().statevector_dqa(g["xi"], int(g["P"]), float(g["dt"]), steps=steps, timings=True)
+    assert abs(exact[0] - 0.3268194661061751) < 1e-13 and ms["mixer"] > 0
+    first, worst = [], []
+    for chi in (4, 10, 32):
+        pl = Plan(21, 17, int(g["P"]), float(g["dt"]), chi)
+        pl.set_patterns(g["xi"][None])
+        pl.set_fourier(g["Uk_FT"], g["fxft"])
+        pl.reset_plus()
+        pl.step(steps)
+        d = np.abs(pl.eps_trace()[0, : steps + 1].real - exact)
+        first.append(float(d[1]))
+        worst.append(float(d.max()))
+    # after one step the truncation error shrinks with chi; later it is O(1e-4) for every chi <= 64 at dt=1
+    # (measured: the dynamics is strongly entangling), so only an envelope is asserted there
+    assert first[0] > first[1] > first[2], first
+    assert max(worst) < 5e-3, worst

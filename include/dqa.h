@@ -113,9 +113,9 @@ int dqa_get_schmidt(dqa_t* h, int inst, int bond, double* s /* [2*chi] */, int* 
 int dqa_get_eps(dqa_t* h, double* eps /* [batch][P+1] complex */);
 int dqa_get_bd_monitor(dqa_t* h, int32_t* bd /* [batch][P*n_xi] */);
 int dqa_get_status(dqa_t* h, int32_t* status /* [batch] */);
-/* [batch][12] u64: Jacobi rotations, Jacobi sweeps, SVDs, QR columns, and the FP64 flops executed by
+/* [batch][16] u64: Jacobi rotations, Jacobi sweeps, SVDs, QR columns, and the FP64 flops executed by
  * the Householder LQ, the Jacobi iteration, the sector QRs and the theta GEMMs (exact loop counts),
- * then SM cycles spent in the LQ and Jacobi phases of the truncation kernel (8, 9). */
+ * then thread-0 clock cycles per phase and CTA counts of k_sector_qr (8..11) and k_lq (12..15). */
 int dqa_get_counters(dqa_t* h, uint64_t* counters, int reset);
 
 /* ensemble moments for the multi-GPU reduction: writes to DEVICE memory (caller-owned,

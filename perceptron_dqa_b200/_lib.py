@@ -284,7 +284,7 @@ class Plan:
         return out
 
     def counters(self, reset=False):
-        out = np.empty((self.batch, 12), dtype=np.uint64)
+        out = np.empty((self.batch, 16), dtype=np.uint64)
         self._ck(self.lib.dqa_get_counters(self._h, _ptr(out), int(reset)))
         return out
 

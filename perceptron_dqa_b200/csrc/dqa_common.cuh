@@ -78,6 +78,39 @@ __device__ __forceinline__ cplx warp_sum(cplx v) {
   return v;
 }
 
+// Sum 16 independent values across the warp with 16 shuffles instead of 80: a butterfly that halves the
+// payload at every stage.  On return lane l holds the warp-wide total of slot (l >> 1) (both lanes of a pair).
+__device__ __forceinline__ double warp_sum16(const double (&v)[16]) {
+  const int lane = threadIdx.x & 31;
+  double a[8], b[4], c[2], dd;
+  const bool h4 = lane & 16, h3 = lane & 8, h2 = lane & 4, h1 = lane & 2;
+#pragma unroll
+  for (int s = 0; s < 8; ++s) {
+    const double send = h4 ? v[s] : v[s + 8];
+    const double keep = h4 ? v[s + 8] : v[s];
+    a[s] = keep + __shfl_xor_sync(DQA_FULL, send, 16);
+  }
+#pragma unroll
+  for (int s = 0; s < 4; ++s) {
+    const double send = h3 ? a[s] : a[s + 4];
+    const double keep = h3 ? a[s + 4] : a[s];
+    b[s] = keep + __shfl_xor_sync(DQA_FULL, send, 8);
+  }
+#pragma unroll
+  for (int s = 0; s < 2; ++s) {
+    const double send = h2 ? b[s] : b[s + 2];
+    const double keep = h2 ? b[s + 2] : b[s];
+    c[s] = keep + __shfl_xor_sync(DQA_FULL, send, 4);
+  }
+  {
+    const double send = h1 ? c[0] : c[1];
+    const double keep = h1 ? c[1] : c[0];
+    dd = keep + __shfl_xor_sync(DQA_FULL, send, 2);
+  }
+  dd += __shfl_xor_sync(DQA_FULL, dd, 1);
+  return dd;  // slot index = 8*h4 + 4*h3 + 2*h2 + h1 = lane >> 1
+}
+
 // ---------------------------------------------------------------------------------
 // FP64 tensor-core tile: D(8x8) += A(8x4) * B(4x8), mma.sync.m8n8k4.f64 (DMMA).
 // Fragment ownership (PTX ISA, .f64 m8n8k4): g = lane>>2, t = lane&3
@@ -152,7 +185,7 @@ struct DqaDev {
   cplx* eps;              // [batch][P+1]
   int* bdmon;             // [batch][P*n_xi]
   int* status;            // [batch]  bit0: non-finite, bit1: zero norm, bit2: Jacobi not converged
-  unsigned long long* counters;  // [batch][DQA_NCNT] rotations, sweeps, svds, qr columns, flops: LQ, Jacobi, sector QR, theta GEMMs; SM cycles: LQ, Jacobi
+  unsigned long long* counters;  // [batch][DQA_NCNT] rotations, sweeps, svds, qr columns, flops: LQ, Jacobi, sector QR, theta GEMMs; thread-0 cycles of sector QR phases (GEMM+load, factor, R/Q out) and #CTAs; of LQ phases (panel, T, trailing) and #CTAs
 };
 
 __host__ __device__ __forceinline__ int dqa_secbase(int N, int n) {
@@ -160,7 +193,7 @@ __host__ __device__ __forceinline__ int dqa_secbase(int N, int n) {
   return (n - 1) * (N + 1) - (n - 1) * n / 2;
 }
 
-#define DQA_NCNT 12  // counters per instance
+#define DQA_NCNT 16  // counters per instance
 
 enum {
   DQA_ST_NONFINITE = 1,

@@ -54,6 +54,25 @@ __device__ __forceinline__ void householder_gen(cplx alpha, double ss, double& b
   }
 }
 
+// Same as householder_gen but with one rsqrt and one reciprocal on the critical path instead of sqrt + 3 divisions.
+__device__ __forceinline__ void householder_gen_fast(cplx alpha, double ss, double& beta, cplx& tau, cplx& scal) {
+  if (ss == 0.0 && alpha.y == 0.0) {
+    beta = alpha.x;
+    tau = cmk(0.0, 0.0);
+    scal = cmk(0.0, 0.0);
+  } else {
+    const double s2 = cabs2(alpha) + ss;
+    const double rs = rsqrt(s2);
+    const double nrm = s2 * rs;
+    const double ib = (alpha.x >= 0.0) ? -rs : rs;  // 1/beta
+    beta = (alpha.x >= 0.0) ? -nrm : nrm;
+    tau = cmk(1.0 - alpha.x * ib, -alpha.y * ib);
+    const double dx = alpha.x - beta;
+    const double inv = 1.0 / fma(dx, dx, alpha.y * alpha.y);
+    scal = cmk(dx * inv, -alpha.y * inv);
+  }
+}
+
 // ---------------------------------------------------------------------------------
 // integer pattern tables (implicit in lib/dQA_utils.py:50-53,106)
 //   hbit = (1-xi)/2, e = 1 - xi*(-1)^s = 2*(hbit^s), q = k*e.  Pure integer arithmetic.
@@ -99,6 +118,9 @@ __global__ void k_init_plus(DqaDev d) {
 // column with no block barrier at all (column j only needs reflectors j..0).
 // shared memory: M (2chi x chi, col-major; column k ends up holding reflector v_k) | tau | beta
 // ---------------------------------------------------------------------------------
+#ifndef SQR_MINB
+#define SQR_MINB 3  // CTAs per SM the 8-slot sector-QR kernel is compiled for
+#endif
 __host__ __device__ inline int sector_qr_maxs(int chi) { return chi <= 8 ? 2 : (chi <= 16 ? 4 : (chi <= 32 ? 8 : (chi <= 48 ? 12 : 16))); }
 __host__ __device__ inline size_t sector_qr_smem(int chi) {  // M has 8*MAXS rows so every register slot has a row
   return sizeof(cplx) * ((size_t)8 * sector_qr_maxs(chi) * chi + chi) + sizeof(double) * chi;
@@ -204,7 +226,7 @@ __device__ __forceinline__ void sqr_apply(cplx (&col)[MAXS], const cplx* vk, cpl
 }
 
 template <int MAXS>
-__global__ void __launch_bounds__(MAXS <= 8 ? 256 : 512, MAXS <= 4 ? 4 : (MAXS == 8 ? 3 : 1)) k_sector_qr(DqaDev d, int n, int mu) {
+__global__ void __launch_bounds__(MAXS <= 8 ? 256 : 512, MAXS <= 4 ? 4 : (MAXS == 8 ? SQR_MINB : 1)) k_sector_qr(DqaDev d, int n, int mu) {
   DQA_DYN_SMEM(smraw);
   const int y = blockIdx.x, inst = blockIdx.y;
   const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarp = nt >> 5;
@@ -229,6 +251,7 @@ __global__ void __launch_bounds__(MAXS <= 8 ? 256 : 512, MAXS <= 4 ? 4 : (MAXS =
   cplx* rout = d.rbuf + (((size_t)inst * 2 + (n & 1)) * d.smax + y) * rsz;
   const cplx* a_site = d.mps + ((size_t)inst * d.N + n) * (2 * rsz);
 
+  const long long tq0 = clock64();
   // ---- M = [R_{yp0} A_0^T ; R_{yp1} A_1^T] with FP64 tensor-core tiles ----
   {
     const int g = lane >> 2, t = lane & 3;
@@ -261,6 +284,7 @@ __global__ void __launch_bounds__(MAXS <= 8 ? 256 : 512, MAXS <= 4 ? 4 : (MAXS =
     col[t] = (has && row < m) ? M[row + j * ldm] : cmk(0.0, 0.0);
   }
   __syncthreads();  // M is reused for the reflectors from here on
+  const long long tq1 = clock64();
   if (warp == 0 && q > 0) sqr_publish<MAXS>(col, 0, m, j, li, M, tau, betas);
   __syncthreads();
   for (int k = 0; k < q; ++k) {
@@ -273,6 +297,7 @@ __global__ void __launch_bounds__(MAXS <= 8 ? 256 : 512, MAXS <= 4 ? 4 : (MAXS =
     __syncthreads();
   }
 
+  const long long tq2 = clock64();
   // ---- R out (row-major q x bl, ld chi), diagonal made non-negative ----
   if (has) {
 #pragma unroll
@@ -320,6 +345,11 @@ __global__ void __launch_bounds__(MAXS <= 8 ? 256 : 512, MAXS <= 4 ? 4 : (MAXS =
       fl += 6ull * (m - k - 1) + 16ull * (unsigned long long)(q - k - 1) * (m - k - 1);  // zung2r column k
     }
     atomicAdd(&d.counters[inst * DQA_NCNT + 6], fl);
+    const long long tq3 = clock64();
+    atomicAdd(&d.counters[inst * DQA_NCNT + 8], (unsigned long long)(tq1 - tq0));
+    atomicAdd(&d.counters[inst * DQA_NCNT + 9], (unsigned long long)(tq2 - tq1));
+    atomicAdd(&d.counters[inst * DQA_NCNT + 10], (unsigned long long)(tq3 - tq2));
+    atomicAdd(&d.counters[inst * DQA_NCNT + 11], 1ull);
   }
 }
 
@@ -478,7 +508,9 @@ __global__ void __launch_bounds__(1024) k_lq(DqaDev d, int l) {
   cplx* lout = d.lbuf + (size_t)inst * (size_t)(2 * chi) * (2 * chi);
   const int ldl = 2 * chi;
 
+  long long tl_panel = 0, tl_t = 0, tl_trail = 0;
   for (int p0 = 0; p0 < k; p0 += pbmax) {
+    const long long tl0 = clock64();
     const int pb = (k - p0) < pbmax ? (k - p0) : pbmax;
     const int n = Q - p0;  // panel columns p0..Q-1
     const cplx* src = (p0 == 0) ? th : wk;
@@ -488,16 +520,21 @@ __global__ void __launch_bounds__(1024) k_lq(DqaDev d, int l) {
     }
     __syncthreads();
     // ---- factor the panel (rows p0..p0+pb-1), unblocked, in shared memory ----
+    // (a column-distributed variant with one fused reduction per reflector was tried and measured slower
+    //  under load: 203 vs 187 ms per step at batch 888)
     for (int i = 0; i < pb; ++i) {
       cplx* row = Vp + i * npad;
       if (warp == 0) {
-        double ss = 0.0;
-        for (int c = i + 1 + lane; c < n; c += 32) ss += cabs2(row[c]);
-        ss = warp_sum(ss);
+        double ss0 = 0.0, ss1 = 0.0;
+        for (int c = i + 1 + lane; c < n; c += 64) {
+          ss0 += cabs2(row[c]);
+          if (c + 32 < n) ss1 += cabs2(row[c + 32]);
+        }
+        const double ss = warp_sum(ss0 + ss1);
         const cplx alpha = row[i];
         double beta;
         cplx t, scal;
-        householder_gen(cconj(alpha), ss, beta, t, scal);
+        householder_gen_fast(cconj(alpha), ss, beta, t, scal);
         const cplx cs = cconj(scal);  // stored vector is conj(v)
         __syncwarp();
         for (int c = i + 1 + lane; c < n; c += 32) row[c] = cmul(row[c], cs);
@@ -511,9 +548,12 @@ __global__ void __launch_bounds__(1024) k_lq(DqaDev d, int l) {
       if (t.x != 0.0 || t.y != 0.0) {
         for (int r = i + 1 + warp; r < pb; r += nwarp) {
           cplx* yr = Vp + r * npad;
-          cplx w = (lane == 0) ? yr[i] : cmk(0.0, 0.0);
-          for (int c = i + 1 + lane; c < n; c += 32) w = cfmac(yr[c], row[c], w);
-          w = warp_sum(w);
+          cplx w0 = (lane == 0) ? yr[i] : cmk(0.0, 0.0), w1 = cmk(0.0, 0.0);
+          for (int c = i + 1 + lane; c < n; c += 64) {
+            w0 = cfmac(yr[c], row[c], w0);
+            if (c + 32 < n) w1 = cfmac(yr[c + 32], row[c + 32], w1);
+          }
+          const cplx w = warp_sum(cadd(w0, w1));
           const cplx tw = cmul(t, w);
           if (lane == 0) yr[i] = csub(yr[i], tw);
           for (int c = i + 1 + lane; c < n; c += 32) yr[c] = cfms(tw, row[c], yr[c]);
@@ -536,73 +576,72 @@ __global__ void __launch_bounds__(1024) k_lq(DqaDev d, int l) {
     }
     __syncthreads();
     const int r_first = p0 + pb;
+    const long long tl1 = clock64();
+    tl_panel += tl1 - tl0;
     if (r_first < mr) {
-      // ---- T of the compact WY form: H_1...H_pb = I - V T V^H ----
-      const int ntask = pb * (pb - 1) / 2;
-      for (int task = warp; task < ntask; task += nwarp) {
-        int i = 1, acc = 0;
-        while (acc + i <= task) {
-          acc += i;
-          ++i;
-        }
-        const int j = task - acc;  // j < i
-        const cplx* vj = Vp + j * npad;
-        const cplx* vi = Vp + i * npad;
-        cplx sacc = cmk(0.0, 0.0);
-        for (int c = i + lane; c < n; c += 32) sacc = cfmac(vj[c], vi[c], sacc);  // v_j^H v_i
-        sacc = warp_sum(sacc);
-        if (lane == 0) Sg[j * LQ_PB + i] = sacc;
-      }
-      __syncthreads();
-      if (tid == 0) {
-        for (int i = 0; i < pb; ++i) {
-          const cplx ti = taus[i];
-          for (int j = 0; j < i; ++j) {
-            cplx acc = cmk(0.0, 0.0);
-            for (int m = j; m < i; ++m) acc = cfma(Tm[j * LQ_PB + m], Sg[m * LQ_PB + i], acc);
-            Tm[j * LQ_PB + i] = cmul(cmk(-ti.x, -ti.y), acc);
-          }
-          Tm[i * LQ_PB + i] = ti;
-        }
-      }
-      __syncthreads();
-      // ---- trailing rows with FP64 tensor-core tiles: W = Y V (split over K), Z = W T, Y -= Z V^H ----
+      const long long tl2 = clock64();
+      tl_t += tl2 - tl1;
+      // ---- trailing rows with FP64 tensor-core tiles --------------------------------------------------
+      // pass 1: W = Y V for every 8-row tile of trailing rows, plus one extra tile with Y = the panel
+      //         itself, which yields S = V^H V (the Gram matrix of the reflectors); K split over warps.
+      // Z = W T without ever forming T: T^{-1} = diag(1/tau) + strict_upper(S), so every row solves
+      //         z_i = tau_i (w_i - sum_{j<i} z_j S[j][i]) independently (forward substitution).
+      // pass 2: Y -= Z V^H.
       const int g = lane >> 2, t4 = lane & 3;
-      const int nrows = mr - r_first, ntr = (nrows + 7) >> 3;
-      int ks = nwarp / ntr;  // K-splits per row tile
+      const int nrows = mr - r_first, ntr = (nrows + 7) >> 3, ntile1 = ntr + 1;
+      int ks = nwarp / ntile1;  // K-splits per tile
       if (ks < 1) ks = 1;
-      if (ks > LQ_MAXW / ntr) ks = LQ_MAXW / ntr > 0 ? LQ_MAXW / ntr : 1;
+      if (ks > LQ_MAXW / ntile1) ks = LQ_MAXW / ntile1 > 0 ? LQ_MAXW / ntile1 : 1;
       const int kchunk = (((n + ks - 1) / ks) + 3) & ~3;
-      for (int task = warp; task < ntr * ks; task += nwarp) {
+      for (int task = warp; task < ntile1 * ks; task += nwarp) {
         const int rt = task / ks, kpart = task % ks;
-        const int r0 = r_first + rt * 8, kbeg = kpart * kchunk;
+        const int kbeg = kpart * kchunk;
         int kend = kbeg + kchunk;
         if (kend > n) kend = n;
         ZTile acc = ztile_zero();
         if (kbeg < kend) {
-          const cplx* ysrc = src + p0 + kbeg;
           const cplx* vsrc = Vp + kbeg;
           const int klen = kend - kbeg;
-          warp_zgemm_8x8(
-              acc, klen,
-              [&](int row, int kk) { return (r0 + row < mr && kk < klen) ? ysrc[(size_t)(r0 + row) * ld + kk] : cmk(0.0, 0.0); },
-              [&](int kk, int col) { return (col < pb && kk < klen) ? cconj(vsrc[col * npad + kk]) : cmk(0.0, 0.0); });
+          if (rt < ntr) {
+            const int r0 = r_first + rt * 8;
+            const cplx* ysrc = src + p0 + kbeg;
+            warp_zgemm_8x8(
+                acc, klen,
+                [&](int row, int kk) { return (r0 + row < mr && kk < klen) ? ysrc[(size_t)(r0 + row) * ld + kk] : cmk(0.0, 0.0); },
+                [&](int kk, int col) { return (col < pb && kk < klen) ? cconj(vsrc[col * npad + kk]) : cmk(0.0, 0.0); });
+          } else {  // the panel against itself: acc[j][i] = sum_c vbar_j[c] conj(vbar_i[c]) = v_j^H v_i = S[j][i]
+            warp_zgemm_8x8(
+                acc, klen,
+                [&](int row, int kk) { return (row < pb && kk < klen) ? vsrc[row * npad + kk] : cmk(0.0, 0.0); },
+                [&](int kk, int col) { return (col < pb && kk < klen) ? cconj(vsrc[col * npad + kk]) : cmk(0.0, 0.0); });
+          }
         }
         cplx* wp = Wp + (size_t)task * 64;
         wp[g * 8 + 2 * t4] = cmk(acc.r0, acc.i0);
         wp[g * 8 + 2 * t4 + 1] = cmk(acc.r1, acc.i1);
       }
       __syncthreads();
-      // Z[row][i] = sum_j (sum_parts W[row][j]) T[j][i]
-      for (int o = tid; o < ntr * 64; o += nt) {
-        const int rt = o >> 6, row = (o >> 3) & 7, i = o & 7;
-        cplx z = cmk(0.0, 0.0);
-        for (int jj = 0; jj <= i && jj < pb; ++jj) {
-          cplx wsum = cmk(0.0, 0.0);
-          for (int kp2 = 0; kp2 < ks; ++kp2) wsum = cadd(wsum, Wp[(size_t)(rt * ks + kp2) * 64 + row * 8 + jj]);
-          z = cfma(wsum, Tm[jj * LQ_PB + i], z);
+      for (int o = tid; o < ntr * 8; o += nt) {  // one thread per trailing row
+        const int rt = o >> 3, row = o & 7;
+        cplx z[LQ_PB];
+#pragma unroll
+        for (int i = 0; i < LQ_PB; ++i) {
+          cplx acc = cmk(0.0, 0.0);
+          if (i < pb) {
+            for (int kp2 = 0; kp2 < ks; ++kp2) acc = cadd(acc, Wp[(size_t)(rt * ks + kp2) * 64 + row * 8 + i]);
+#pragma unroll
+            for (int jj = 0; jj < LQ_PB; ++jj) {
+              if (jj < i) {
+                cplx sji = cmk(0.0, 0.0);
+                for (int kp2 = 0; kp2 < ks; ++kp2) sji = cadd(sji, Wp[(size_t)(ntr * ks + kp2) * 64 + jj * 8 + i]);
+                acc = cfms(z[jj], sji, acc);
+              }
+            }
+            acc = cmul(taus[i], acc);
+          }
+          z[i] = acc;
+          Zs[o * 8 + i] = acc;
         }
-        Zs[o] = (i < pb) ? z : cmk(0.0, 0.0);
       }
       __syncthreads();
       const int ntc = (n + 7) >> 3;
@@ -628,6 +667,7 @@ __global__ void __launch_bounds__(1024) k_lq(DqaDev d, int l) {
           }
         }
       }
+      tl_trail += clock64() - tl2;
     }
     __syncthreads();
   }
@@ -639,6 +679,10 @@ __global__ void __launch_bounds__(1024) k_lq(DqaDev d, int l) {
     unsigned long long lq = 0;
     for (int kk = 0; kk < k; ++kk) lq += 10ull * (Q - kk - 1) + 16ull * (unsigned long long)(mr - kk - 1) * (Q - kk);
     atomicAdd(&d.counters[inst * DQA_NCNT + 4], lq);
+    atomicAdd(&d.counters[inst * DQA_NCNT + 12], (unsigned long long)tl_panel);
+    atomicAdd(&d.counters[inst * DQA_NCNT + 13], (unsigned long long)tl_t);
+    atomicAdd(&d.counters[inst * DQA_NCNT + 14], (unsigned long long)tl_trail);
+    atomicAdd(&d.counters[inst * DQA_NCNT + 15], 1ull);
   }
 }
 

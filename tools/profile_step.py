@@ -48,7 +48,8 @@ def main():
     out = dict(cfg=vars(a), warm_s=t1 - t0, ms_per_step={k: v / a.steps for k, v in ms.items()}, launches=n,
                wall_s_per_step_profiled=(t2 - t1) / a.steps, wall_s_per_step=(t3 - t2) / a.steps,
                rotations_per_svd=float(cnt[0]) / max(1, int(cnt[2])), sweeps_per_svd=float(cnt[1]) / max(1, int(cnt[2])),
-               bonds=pl.bonds(0).tolist(),                flops_per_step_per_inst={k: float(cnt[i]) / a.steps / a.batch for k, i in (('lq', 4), ('jacobi', 5), ('sector_qr', 6), ('theta', 7))}, fp64_peak_tflops=pl.fp64_peak_tflops())
+               bonds=pl.bonds(0).tolist(), sqr_cycles_per_cta={k: float(cnt[i]) / max(1.0, float(cnt[11])) for k, i in (('gemm_load', 8), ('factor', 9), ('out_formq', 10))},
+               lq_cycles_per_cta={k: float(cnt[i]) / max(1.0, float(cnt[15])) for k, i in (('panel', 12), ('tmat', 13), ('trailing', 14))},                flops_per_step_per_inst={k: float(cnt[i]) / a.steps / a.batch for k, i in (('lq', 4), ('jacobi', 5), ('sector_qr', 6), ('theta', 7))}, fp64_peak_tflops=pl.fp64_peak_tflops())
     print(json.dumps(out))
 
 

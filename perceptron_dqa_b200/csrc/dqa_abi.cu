@@ -20,6 +20,12 @@
 #define OPS_THREADS 1024
 #endif
 
+// template instances with a comma in their argument list, named so they can pass through macros
+static void (*const KJ_0S)(DqaDev, int, int, int) = k_jacobi<0, true>;
+static void (*const KJ_0G)(DqaDev, int, int, int) = k_jacobi<0, false>;
+static void (*const KJ_4S)(DqaDev, int, int, int) = k_jacobi<4, true>;
+static void (*const KJ_8S)(DqaDev, int, int, int) = k_jacobi<8, true>;
+
 struct dqa_handle {
   dqa_config cfg;
   DqaDev dev;
@@ -201,9 +207,10 @@ extern "C" int dqa_create(dqa_t** out, const dqa_config* cfg) {
   CK(cudaFuncSetAttribute(k_sector_qr<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sector_qr_smem(c.chi)));
   CK(cudaFuncSetAttribute(k_sector_qr<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sector_qr_smem(c.chi)));
   CK(cudaFuncSetAttribute(k_sector_qr<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sector_qr_smem(c.chi)));
-  CK(cudaFuncSetAttribute(k_jacobi<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)svd_smem(c.chi)));
-  CK(cudaFuncSetAttribute(k_jacobi<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)svd_smem(c.chi)));
-  CK(cudaFuncSetAttribute(k_jacobi<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)svd_smem(c.chi)));
+  CK(cudaFuncSetAttribute(KJ_0S, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)svd_smem(c.chi)));
+  CK(cudaFuncSetAttribute(KJ_0G, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)svd_smem(c.chi)));
+  CK(cudaFuncSetAttribute(KJ_4S, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)svd_smem(c.chi)));
+  CK(cudaFuncSetAttribute(KJ_8S, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)svd_smem(c.chi)));
   CK(cudaFuncSetAttribute(k_lq, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lq_smem(h->dev.qmax, c.chi, h->dev.lq_pb)));
   CK(cudaFuncSetAttribute(k_energy, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)energy_smem(c.chi)));
   CK(cudaFuncSetAttribute(k_theta, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(cplx) * c.chi * c.chi)));
@@ -397,9 +404,10 @@ static int launch_truncate(dqa_t* h, int p, int mu) {
     {
       // register-cached variant needs one pass per round (4 pairs per warp) and 2chi <= 8*RS rows
       const bool one_pass = (h->t_svd / 32) * 4 >= d.chi;
-      if (one_pass && d.chi <= 16 && !h->jac_nocache) HL(k_jacobi<4>, dim3(d.batch), dim3(h->t_svd), svd_smem(d.chi), h->stream, d, l, mu, p);
-      else if (one_pass && d.chi <= 32 && h->jac_cache32) HL(k_jacobi<8>, dim3(d.batch), dim3(h->t_svd), svd_smem(d.chi), h->stream, d, l, mu, p);
-      else HL(k_jacobi<0>, dim3(d.batch), dim3(h->t_svd), svd_smem(d.chi), h->stream, d, l, mu, p);
+      if (one_pass && d.chi <= 16 && !h->jac_nocache) HL(KJ_4S, dim3(d.batch), dim3(h->t_svd), svd_smem(d.chi), h->stream, d, l, mu, p);
+      else if (one_pass && d.chi <= 32 && h->jac_cache32) HL(KJ_8S, dim3(d.batch), dim3(h->t_svd), svd_smem(d.chi), h->stream, d, l, mu, p);
+      else if (svd_l_in_smem(d.chi)) HL(KJ_0S, dim3(d.batch), dim3(h->t_svd), svd_smem(d.chi), h->stream, d, l, mu, p);
+      else HL(KJ_0G, dim3(d.batch), dim3(h->t_svd), svd_smem(d.chi), h->stream, d, l, mu, p);
     }
     prof_b(h);
   }

@@ -722,15 +722,17 @@ __device__ __forceinline__ void rr_pair(int n, int round, int idx, int& p, int& 
 }
 
 #define JAC_UN 4
-template <int RS>  // RS > 0: one pass per round, the pair's rows (li+8t, t<RS) stay in registers between dot and rotation
+template <int RS, bool LSM>  // RS > 0: one pass per round, the pair's rows (li+8t, t<RS) stay in registers between dot and
+                             // rotation; LSM: L lives in shared memory (compile-time, so its accesses are LDS/STS)
 __global__ void __launch_bounds__(512) k_jacobi(DqaDev d, int l, int mu, int p_step) {
   DQA_DYN_SMEM(smraw);
   const int inst = blockIdx.x, tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarp = nt >> 5;
   const int chi = d.chi;
   const size_t rsz = (size_t)chi * chi;
-  const bool lsm = svd_l_in_smem(chi);
+  constexpr bool lsm = LSM;
   cplx* lglob = d.lbuf + (size_t)inst * (size_t)(2 * chi) * (2 * chi);
-  cplx* L = lsm ? (cplx*)smraw : lglob;
+  cplx* L;
+  if (LSM) L = (cplx*)smraw; else L = lglob;
   double* sig = (double*)(smraw + (lsm ? sizeof(cplx) * (size_t)(2 * chi) * (2 * chi) : 0));
   double* ssorted = sig + 2 * chi;
   int* order = (int*)(ssorted + 2 * chi + 8);

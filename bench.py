@@ -332,6 +332,18 @@ def run_ours(a):
                            "frac": float(sum(flops.values())) / (sum(fam_ms.values()) * 1e-3) / 1e12 / peak if peak else None},
             "rotations_per_svd": float(cnt[0]) / max(1.0, float(cnt[2])), "sweeps_per_svd": float(cnt[1]) / max(1.0, float(cnt[2])),
         }
+        # the HBM side of the roofline, to show the step is not bandwidth bound: algorithmic bytes = the MPS read and
+        # written once per pattern sub-step and once for mixer+energy, against the pool's measured copy bandwidth
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+            hbm_peak, hbm_src = float(peaks["hbm_gbs"]), "MEASURED_PEAKS.json"
+        except Exception:
+            hbm_peak, hbm_src = 6650.0, "fallback of B200_PROFILING.md"
+        s_bytes = sum(16 * 2 * int(bonds[i]) * int(bonds[i + 1]) for i in range(a.n))
+        alg_bytes = 2.0 * (a.nxi + 1) * s_bytes * B
+        step_s = sum(fam_ms.values()) * 1e-3
+        line["roofline"]["hbm_view"] = {"algorithmic_bytes_per_step": alg_bytes, "achieved_gbs": alg_bytes / step_s / 1e9,
+                                        "peak_gbs": hbm_peak, "peak_source": hbm_src, "frac": alg_bytes / step_s / 1e9 / hbm_peak}
     if rank == 0 and B > 1:
         # latency view: one realisation alone on the GPU
         o1 = mydQA(xi[0], P=a.P, dt=a.dt, max_bond=a.chi, device=local)

@@ -78,6 +78,7 @@ int dqa_get_index_tensors(dqa_t* h, int inst, uint8_t* hbit, int32_t* e, int32_t
 int dqa_reset_plus(dqa_t* h);            /* |+>^N, pp=0, eps[0] = eps(0)               */
 int dqa_step(dqa_t* h, int nsteps);      /* nsteps x single_step(); DQA_ENUMERIC if any
                                             instance's status word is non-zero          */
+int dqa_step_async(dqa_t* h, int nsteps); /* same, but no host sync / status check (overlap handles on streams) */
 int dqa_get_step(const dqa_t* h, int* pp);
 int dqa_set_step(dqa_t* h, int pp);
 

@@ -47,6 +47,7 @@ _SIGS = {
     "dqa_get_index_tensors": ([_P, C.c_int, _P, _P, _P], C.c_int),
     "dqa_reset_plus": ([_P], C.c_int),
     "dqa_step": ([_P, C.c_int], C.c_int),
+    "dqa_step_async": ([_P, C.c_int], C.c_int),
     "dqa_get_step": ([_P, C.POINTER(C.c_int)], C.c_int),
     "dqa_set_step": ([_P, C.c_int], C.c_int),
     "dqa_apply_pattern": ([_P, C.c_int, C.c_int], C.c_int),
@@ -191,6 +192,9 @@ class Plan:
 
     def step(self, nsteps=1):
         self._ck(self.lib.dqa_step(self._h, nsteps))
+
+    def step_async(self, nsteps=1):
+        self._ck(self.lib.dqa_step_async(self._h, nsteps))
 
     @property
     def pp(self):

@@ -488,7 +488,11 @@ static int check_status(dqa_t* h) {
   return DQA_OK;
 }
 
-extern "C" int dqa_step(dqa_t* h, int nsteps) {
+static int step_impl(dqa_t* h, int nsteps, bool check);
+extern "C" int dqa_step(dqa_t* h, int nsteps) { return step_impl(h, nsteps, true); }
+// same launches, no host synchronisation and no status check: lets several handles on different streams overlap
+extern "C" int dqa_step_async(dqa_t* h, int nsteps) { return step_impl(h, nsteps, false); }
+static int step_impl(dqa_t* h, int nsteps, bool check) {
   NEED_READY();
   if (nsteps < 0 || h->pp + nsteps > h->cfg.P) return fail(h, DQA_EINVAL, "step %d + %d exceeds P=%d", h->pp, nsteps, h->cfg.P);
   for (int it = 0; it < nsteps; ++it) {
@@ -507,7 +511,7 @@ extern "C" int dqa_step(dqa_t* h, int nsteps) {
     if (rc) return rc;
     h->pp++;
   }
-  return check_status(h);
+  return check ? check_status(h) : DQA_OK;
 }
 
 extern "C" int dqa_energy(dqa_t* h, double* eps) {

@@ -176,6 +176,43 @@ def test_p2_full_c1_envelope(factory):
     assert not pl.status().any()
 
 
+def test_p4_reference_stored_curves():
+    """P4 envelopes against the vectors the reference itself ships (tests/golden/reference_curves.npz, copied by
+    oracle/make_reference_curves.py): they were produced in complex64 (jax without x64) or by the quimb implementation,
+    and the trajectory is chaotic, so they pin the run to ~1e-3, not to 1e-10."""
+    import os
+
+    from helpers import GOLDEN
+    from perceptron_dqa_b200.dQA_mps import mydQA
+
+    r = np.load(os.path.join(GOLDEN, "reference_curves.npz"))
+    g = golden("c1_n12_chi10")
+    o = mydQA(g["xi"], P=100, dt=0.5, max_bond=10)
+    o.init_fourier()
+    o.run(print_info=False)
+    e = o.eps[0]
+    assert np.abs(e - r["numpy_9_12_P100_dt05_bd10"]).max() < 2e-3      # data/benchmark/numpy_9-12_loss/dt0.5_bd10.npy
+    assert np.abs(e - r["quimb_9_12_P100_dt05_bd10"]).max() < 3e-3      # data/benchmark/quimb_9-12_loss_dt0.5_bd10.npy
+    assert abs(e[-1].real - 3.434725e-3) < 3e-4 and abs(e[-1].real - 3.382827131021171e-3) < 3e-4
+    # N=21, N_xi=17, P=100, dt=1.0: numpy_17-21.csv row "100,1.0" (5.107701e-3) and quimb_17-21.csv (5.176112e-3)
+    xi = r["patterns_17_21_1"]
+    for chi, want in ((10, 5.107701e-3), (20, float(r["numpy_17_21_P100_dt1_bd20"][-1].real))):
+        o = mydQA(xi, P=100, dt=1.0, max_bond=chi)
+        o.init_fourier()
+        o.run(print_info=False)
+        assert abs(o.eps[0, -1].real - want) < 5e-4, (chi, o.eps[0, -1].real, want)
+        assert np.abs(o.eps.imag).max() < 1e-12 and not o.plan.status().any()
+    tq = r["table_quimb_17_21"]
+    q = float(tq[(tq[:, 0] == 100) & (np.abs(tq[:, 1] - 1.0) < 1e-9), 3][0])
+    assert abs(q - 5.176112e-3) < 1e-8
+    # N=15, dt=1.2 (dQA_mps.py's own __main__ example): a more chaotic point, looser envelope
+    o = mydQA(r["patterns_12_15"], P=100, dt=1.2, max_bond=10)
+    o.init_fourier()
+    o.run(print_info=False)
+    s15 = r["numpy_12_15_P100_dt12_bd10"]
+    assert np.abs(o.eps[0] - s15).max() < 2e-2 and abs(o.eps[0, -1].real - s15[-1].real) < 3e-3
+
+
 def test_final_state_c1(factory):
     ps.check_final_state(factory, "c1_n12_chi10", 5)
 

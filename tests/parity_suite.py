@@ -159,3 +159,27 @@ def check_batch_consistency(factory, name, steps=2, batch=3):
     ref.init_fourier()
     ref.run(steps=steps)
     assert np.abs(eps[1] - np.array([l[1] for l in ref.loss])).max() < 1e-11
+
+
+def check_small_edge_cases(factory, cases=None):
+    """Minimal sizes and odd shapes: N=2..5, chi=1..4 (chi=1 is a product-state projection), one or several
+    patterns, P as small as 1, against the oracle run on the fly (the oracle is cheap here)."""
+    rng = np.random.default_rng(11)
+    cases = cases or [(2, 1, 1, 1), (2, 2, 2, 3), (3, 1, 1, 2), (3, 2, 2, 2), (4, 3, 4, 3), (5, 2, 3, 4), (5, 4, 1, 2), (6, 3, 8, 2)]
+    for (n, n_xi, chi, P) in cases:
+        xi = (2 * rng.integers(0, 2, size=(n_xi, n)) - 1).astype(np.int8)
+        dt = 0.6
+        ref = O.OracleDQA(xi, P, dt, chi, fast_loss=True)
+        ref.init_fourier()
+        ref.run()
+        pl = factory(n, n_xi, P, dt, chi, 1)
+        pl.set_patterns(xi[None])
+        pl.set_fourier(ref.Uk_FT, ref.fxft)
+        pl.reset_plus()
+        pl.step(P)
+        got = pl.eps_trace()[0]
+        want = np.array([l[1] for l in ref.loss])
+        assert np.abs(got - want).max() < 1e-11, (n, n_xi, chi, P, np.abs(got - want).max())
+        assert list(pl.bd_monitor()[0]) == ref.bd_monitor, (n, n_xi, chi, P)
+        assert abs(O.fidelity_defect(pl.get_mps(0), ref.psi)) < 1e-11
+        assert not pl.status().any()

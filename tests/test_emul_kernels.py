@@ -47,6 +47,10 @@ def test_batch(factory):
     ps.check_batch_consistency(factory, "n7_chi4", steps=1, batch=3)
 
 
+def test_small_edge_cases(factory):
+    ps.check_small_edge_cases(factory)
+
+
 def test_teacher_forced_n12_one_substep(factory):
     ps.check_teacher_forced(factory, "c1_n12_chi10", max_snaps=1)
 

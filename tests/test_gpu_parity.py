@@ -221,6 +221,43 @@ def test_batch_independence(factory):
     ps.check_batch_consistency(factory, "c1_n12_chi10", steps=2, batch=3)
 
 
+def test_c4_synthetic_realisations_against_oracle(factory):
+    """C4: iid +-1 patterns from default_rng(20230317), N=21, N_xi=17.  Two realisations evolved as one batch
+    on the device vs the numpy oracle run on the host cores of this box, first two steps (pre-chaotic: 1e-11), and the
+    ensemble moments the all-reduce would carry."""
+    rng = np.random.default_rng(20230317)
+    table = (2 * rng.integers(0, 2, size=(1024, 17, 21)) - 1).astype(np.int8)
+    xi = table[[3, 700]]
+    P, dt, chi, steps = 100, 1.0, 10, 2
+    pl = factory(21, 17, P, dt, chi, 2)
+    uk, fx = O.fourier_tables(21, P, dt)
+    pl.set_patterns(xi)
+    pl.set_fourier(uk, fx)
+    pl.reset_plus()
+    pl.step(steps)
+    eps = pl.eps_trace()[:, : steps + 1]
+    for b in range(2):
+        ref = O.OracleDQA(xi[b], P, dt, chi, fast_loss=True)
+        ref.init_fourier()
+        ref.run(steps=steps)
+        want = np.array([l[1] for l in ref.loss])
+        assert np.abs(eps[b] - want).max() < 1e-11
+        assert abs(O.fidelity_defect(pl.get_mps(b), ref.psi)) < 1e-11
+    import torch
+
+    from perceptron_dqa_b200.ensemble import finalize_moments
+
+    mom = torch.zeros(3 * (P + 1), dtype=torch.float64, device="cuda")
+    pl.ensemble_moments_into(mom.data_ptr())
+    torch.cuda.synchronize()
+    mean, _sem, cnt = finalize_moments(mom.cpu().numpy())
+    assert cnt[0] == 2 and np.abs(mean[: steps + 1] - eps.real.mean(0)).max() < 1e-15
+
+
+def test_small_edge_cases(factory):
+    ps.check_small_edge_cases(factory)
+
+
 def test_driver_class_matches_fixture():
     """The mydQA drop-in: construct -> init_fourier -> run -> loss[-1][1] (benchmarker-mps.py:32-43)."""
     from perceptron_dqa_b200.dQA_mps import mydQA

@@ -25,6 +25,9 @@ static void (*const KJ_0S)(DqaDev, int, int, int) = k_jacobi<0, true>;
 static void (*const KJ_0G)(DqaDev, int, int, int) = k_jacobi<0, false>;
 static void (*const KJ_4S)(DqaDev, int, int, int) = k_jacobi<4, true>;
 static void (*const KJ_8S)(DqaDev, int, int, int) = k_jacobi<8, true>;
+static void (*const KJ_Y2)(DqaDev, int, int, int) = k_jacobi_sys<2>;
+static void (*const KJ_Y4)(DqaDev, int, int, int) = k_jacobi_sys<4>;
+static void (*const KJ_Y8)(DqaDev, int, int, int) = k_jacobi_sys<8>;
 
 struct dqa_handle {
   dqa_config cfg;
@@ -39,7 +42,7 @@ struct dqa_handle {
   bool have_patterns, have_fourier, have_state;
   int t_qr, t_theta, t_svd, t_energy;  // block sizes
   int t_lq;
-  bool jac_nocache, jac_cache32;
+  bool jac_nocache, jac_cache32, jac_sys;
   char err[512];
   // profiling
   bool profiling;
@@ -201,6 +204,10 @@ extern "C" int dqa_create(dqa_t** out, const dqa_config* cfg) {
   }
   h->t_energy = c.chi <= 8 ? 64 : 256;
 #endif
+  {
+    const char* env = getenv("DQA_JAC_SYS");  // 0: use the shared-memory-resident Jacobi for every chi
+    h->jac_sys = !(env && atoi(env) == 0);
+  }
   CK(cudaSetDevice(c.device));
   CK(cudaFuncSetAttribute(k_sector_qr<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sector_qr_smem(c.chi)));
   CK(cudaFuncSetAttribute(k_sector_qr<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sector_qr_smem(c.chi)));
@@ -211,6 +218,11 @@ extern "C" int dqa_create(dqa_t** out, const dqa_config* cfg) {
   CK(cudaFuncSetAttribute(KJ_0G, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)svd_smem(c.chi)));
   CK(cudaFuncSetAttribute(KJ_4S, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)svd_smem(c.chi)));
   CK(cudaFuncSetAttribute(KJ_8S, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)svd_smem(c.chi)));
+  if (c.chi <= 32) {
+    CK(cudaFuncSetAttribute(KJ_Y2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)svd_smem(c.chi)));
+    CK(cudaFuncSetAttribute(KJ_Y4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)svd_smem(c.chi)));
+    CK(cudaFuncSetAttribute(KJ_Y8, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)svd_smem(c.chi)));
+  }
   CK(cudaFuncSetAttribute(k_lq, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lq_smem(h->dev.qmax, c.chi, h->dev.lq_pb)));
   CK(cudaFuncSetAttribute(k_energy, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)energy_smem(c.chi)));
   CK(cudaFuncSetAttribute(k_theta, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(cplx) * c.chi * c.chi)));
@@ -404,7 +416,11 @@ static int launch_truncate(dqa_t* h, int p, int mu) {
     {
       // register-cached variant needs one pass per round (4 pairs per warp) and 2chi <= 8*RS rows
       const bool one_pass = (h->t_svd / 32) * 4 >= d.chi;
-      if (one_pass && d.chi <= 16 && !h->jac_nocache) HL(KJ_4S, dim3(d.batch), dim3(h->t_svd), svd_smem(d.chi), h->stream, d, l, mu, p);
+      const int t_sys = 32 * ((d.chi + 3) / 4);  // one 8-lane group per column pair
+      if (h->jac_sys && d.chi <= 8) HL(KJ_Y2, dim3(d.batch), dim3(t_sys), svd_smem(d.chi), h->stream, d, l, mu, p);
+      else if (h->jac_sys && d.chi <= 16) HL(KJ_Y4, dim3(d.batch), dim3(t_sys), svd_smem(d.chi), h->stream, d, l, mu, p);
+      else if (h->jac_sys && d.chi <= 32) HL(KJ_Y8, dim3(d.batch), dim3(t_sys), svd_smem(d.chi), h->stream, d, l, mu, p);
+      else if (one_pass && d.chi <= 16 && !h->jac_nocache) HL(KJ_4S, dim3(d.batch), dim3(h->t_svd), svd_smem(d.chi), h->stream, d, l, mu, p);
       else if (one_pass && d.chi <= 32 && h->jac_cache32) HL(KJ_8S, dim3(d.batch), dim3(h->t_svd), svd_smem(d.chi), h->stream, d, l, mu, p);
       else if (svd_l_in_smem(d.chi)) HL(KJ_0S, dim3(d.batch), dim3(h->t_svd), svd_smem(d.chi), h->stream, d, l, mu, p);
       else HL(KJ_0G, dim3(d.batch), dim3(h->t_svd), svd_smem(d.chi), h->stream, d, l, mu, p);

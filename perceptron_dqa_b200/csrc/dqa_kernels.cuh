@@ -721,6 +721,83 @@ __device__ __forceinline__ void rr_pair(int n, int round, int idx, int& p, int& 
   }
 }
 
+// Shared tail of the Jacobi kernels: singular values of the kc stored columns (k of them real, kc - k zero padding),
+// ordering, the reference's trim rule (lib/tenn.py:317-354), counters, and the new left-orthonormal site tensor.
+__device__ __forceinline__ void jacobi_tail(const DqaDev& d, int inst, int l, int mu, int p_step, const cplx* L, int ldl, int mr, int k,
+                                            int kc, double* sig, double* ssorted, int* order, int* sh_i, int* bond, int converged,
+                                            int sweeps, unsigned long long nrot_total) {
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarp = nt >> 5;
+  const int chi = d.chi;
+  const size_t rsz = (size_t)chi * chi;
+  for (int j = warp; j < kc; j += nwarp) {
+    double a = 0.0;
+    for (int r = lane; r < mr; r += 32) a += cabs2(L[r + j * ldl]);
+    a = warp_sum(a);
+    if (lane == 0) sig[j] = sqrt(a);
+  }
+  for (int j = tid; j < kc; j += nt) order[j] = j;
+  __syncthreads();
+  for (int j = tid; j < kc; j += nt) {
+    const double sj = sig[j];
+    int rank = 0;
+    for (int i = 0; i < kc; ++i) {
+      const double si = sig[i];
+      rank += (si > sj) || (si == sj && i < j);
+    }
+    if (sj == sj) {  // NaN keeps the identity slot
+      order[rank] = j;
+      ssorted[rank] = sj;
+    } else {
+      ssorted[j] = sj;
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    double tot = 0.0;
+    for (int i = 0; i < k; ++i) tot += ssorted[i] * ssorted[i];
+    const double thr = (1.0 - d.cutoff) * tot;
+    double csp = 0.0, ckeep = 0.0;
+    int cnt = 0;
+    for (int i = 0; i < k; ++i) {
+      csp += ssorted[i] * ssorted[i];
+      if (csp < thr) cnt++;
+    }
+    int n_chi = cnt + 1;
+    if (n_chi < 1) n_chi = 1;
+    if (n_chi > chi) n_chi = chi;
+    if (n_chi > k) n_chi = k;
+    for (int i = 0; i < n_chi; ++i) ckeep += ssorted[i] * ssorted[i];
+    double sc = 1.0;
+    int st = 0;
+    if (!(tot == tot) || tot > 1e300) st |= DQA_ST_NONFINITE;
+    if (tot == 0.0) st |= DQA_ST_ZERONORM;
+    if (!converged) st |= DQA_ST_NOCONV;
+    if (n_chi < k && ckeep > 0.0) sc = sqrt(tot / ckeep);
+    if (st) atomicOr(&d.status[inst], st);
+    sh_i[1] = n_chi;
+    d.scale[inst] = sc;
+    bond[l + 1] = n_chi;
+    d.nsv[inst * d.N + l] = k;
+    atomicAdd(&d.counters[inst * DQA_NCNT + 0], nrot_total);
+    atomicAdd(&d.counters[inst * DQA_NCNT + 1], (unsigned long long)sweeps);
+    atomicAdd(&d.counters[inst * DQA_NCNT + 2], 1ull);
+    atomicAdd(&d.counters[inst * DQA_NCNT + 5],
+              (unsigned long long)sweeps * (unsigned long long)(k * (k - 1) / 2) * 8ull * mr + nrot_total * 20ull * mr +
+                  (unsigned long long)sweeps * 4ull * mr * k);
+    if (l == d.N - 1) d.bdmon[(size_t)inst * d.P * d.n_xi + (size_t)p_step * d.n_xi + mu] = bond[d.N / 2];
+  }
+  __syncthreads();
+  const int n_chi = sh_i[1];
+  for (int i = tid; i < k; i += nt) d.schmidt[((size_t)inst * d.N + l) * (2 * chi) + i] = ssorted[i];
+  cplx* site = d.mps + ((size_t)inst * d.N + l) * (2 * rsz);
+  for (int i = tid; i < mr * n_chi; i += nt) {
+    const int b = i % n_chi, r = i / n_chi;
+    const double sv = ssorted[b];
+    const double inv = sv > 0.0 ? 1.0 / sv : 0.0;
+    site[r * chi + b] = cscale(L[r + order[b] * ldl], inv);
+  }
+}
+
 #define JAC_UN 4
 template <int RS, bool LSM>  // RS > 0: one pass per round, the pair's rows (li+8t, t<RS) stay in registers between dot and
                              // rotation; LSM: L lives in shared memory (compile-time, so its accesses are LDS/STS)
@@ -728,8 +805,7 @@ __global__ void __launch_bounds__(512) k_jacobi(DqaDev d, int l, int mu, int p_s
   DQA_DYN_SMEM(smraw);
   const int inst = blockIdx.x, tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarp = nt >> 5;
   const int chi = d.chi;
-  const size_t rsz = (size_t)chi * chi;
-  constexpr bool lsm = LSM;
+    constexpr bool lsm = LSM;
   cplx* lglob = d.lbuf + (size_t)inst * (size_t)(2 * chi) * (2 * chi);
   cplx* L;
   if (LSM) L = (cplx*)smraw; else L = lglob;
@@ -922,74 +998,196 @@ __global__ void __launch_bounds__(512) k_jacobi(DqaDev d, int l, int mu, int p_s
     __syncthreads();
   }
 
-  // ---- singular values, ordering, trim rule ------------------------------------------
-  for (int j = warp; j < k; j += nwarp) {
-    double a = 0.0;
-    for (int r = lane; r < mr; r += 32) a += cabs2(L[r + j * ldl]);
-    a = warp_sum(a);
-    if (lane == 0) sig[j] = sqrt(a);
+  jacobi_tail(d, inst, l, mu, p_step, L, ldl, mr, k, k, sig, ssorted, order, sh_i, bond, converged, sweeps, nrot_total);
+}
+
+// ---------------------------------------------------------------------------------
+// k_jacobi_sys: the same SVD + trim as k_jacobi for 2chi <= 8*RS rows, as a systolic array.
+// An 8-lane group owns two columns for the WHOLE iteration, in registers (RS rows per lane
+// and column).  Pairing follows the odd-even transposition ordering: in even rounds a group
+// orthogonalises its own two columns and passes one to the right-hand neighbour, in odd
+// rounds it orthogonalises the received column against the one it kept and passes one back
+// to the left; the columns at the two ends of the line idle in odd rounds (group 0 holds
+// both and only exchanges their roles), which is what makes every pair meet exactly once in
+// a sweep of 2*groups rounds.  Per pair and round one column crosses shared memory (one
+// store + one load) instead of the three loads + one store per column of k_jacobi, which is
+// shared-memory-bandwidth bound.  Cached squared norms travel with the columns.  Rotation
+// parameters without a division:  delta=(b-a)/2, r=hypot(delta,|g|), u=r+|delta|,
+// q=1/sqrt(2ru):  c=uq, s e^{-i phi}=sign(delta) q conj(g), t|g|=2|g|^2 r q^2; the second
+// column of a pair is left with the phase e^{i phi} (a gauge of the singular vector).
+// shared: exchange buffers 2 x (groups x mr), reused for the final columns | sig | xn/ssorted | order | sh_i
+// ---------------------------------------------------------------------------------
+template <int RS>
+__global__ void __launch_bounds__(RS * 32, RS >= 8 ? 2 : (RS >= 4 ? 6 : 8)) k_jacobi_sys(DqaDev d, int l, int mu, int p_step) {
+  DQA_DYN_SMEM(smraw);
+  const int inst = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
+  const int chi = d.chi;
+  const cplx* lglob = d.lbuf + (size_t)inst * (size_t)(2 * chi) * (2 * chi);
+  cplx* X = (cplx*)smraw;
+  double* sig = (double*)(smraw + sizeof(cplx) * (size_t)(2 * chi) * (2 * chi));
+  double* ssorted = sig + 2 * chi;
+  int* order = (int*)(ssorted + 2 * chi + 8);
+  int* sh_i = order + 2 * chi;  // [0]=rotation count, [1]=n_chi, [2]=some rotated pair was above the quadratic threshold
+  int* bond = d.bond + inst * (d.N + 1);
+  const int mr = 2 * bond[l];
+  const int* qd1 = d.qdim + ((size_t)inst * (d.N + 1) + (l + 1)) * d.smax;
+  const int Q = qdim_prefix(qd1, d.N - l);
+  const int k = mr < Q ? mr : Q;
+  const int kp = k + (k & 1), h = kp >> 1;  // h groups hold the kp columns (one zero column when k is odd)
+  const int g = tid >> 3, li = lane & 7;
+  const bool act = g < h;
+  double* xn = ssorted;  // [2][chi] squared norms in flight (ssorted is only used by the tail)
+
+  // A = column 2g+1, B = column 2g, straight from the L2-resident factor
+  cplx A[RS], B[RS];
+#pragma unroll
+  for (int t = 0; t < RS; ++t) {
+    const int r = li + 8 * t;
+    const bool in = act && r < mr;
+    B[t] = (in && 2 * g < k) ? lglob[r + (size_t)(2 * g) * (2 * chi)] : cmk(0.0, 0.0);
+    A[t] = (in && 2 * g + 1 < k) ? lglob[r + (size_t)(2 * g + 1) * (2 * chi)] : cmk(0.0, 0.0);
   }
-  for (int j = tid; j < k; j += nt) order[j] = j;
-  __syncthreads();
-  for (int j = tid; j < k; j += nt) {
-    const double sj = sig[j];
-    int rank = 0;
-    for (int i = 0; i < k; ++i) {
-      const double si = sig[i];
-      rank += (si > sj) || (si == sj && i < j);
+  const int gr = (g + 1 < h) ? g + 1 : 0, gl = (g > 0) ? g - 1 : h - 1;  // ring neighbours (only the parked column wraps)
+  const size_t bufsz = (size_t)h * mr;
+  const double tol = sqrt((double)mr) * 2.220446049250313e-16, tol2 = tol * tol;
+  int sweeps = 0, converged = (k <= 1);
+  unsigned long long nrot_total = 0;
+  for (int sweep = 0; sweep < d.max_sweeps && !converged; ++sweep) {
+    double nA = 0.0, nB = 0.0;  // exact squared norms once per sweep, updated by the rotation formulas in between
+#pragma unroll
+    for (int t = 0; t < RS; ++t) {
+      nA += cabs2(A[t]);
+      nB += cabs2(B[t]);
     }
-    if (sj == sj) {  // NaN keeps the identity slot
-      order[rank] = j;
-      ssorted[rank] = sj;
-    } else {
-      ssorted[j] = sj;
+    nA += __shfl_xor_sync(DQA_FULL, nA, 4);
+    nB += __shfl_xor_sync(DQA_FULL, nB, 4);
+    nA += __shfl_xor_sync(DQA_FULL, nA, 2);
+    nB += __shfl_xor_sync(DQA_FULL, nB, 2);
+    nA += __shfl_xor_sync(DQA_FULL, nA, 1);
+    nB += __shfl_xor_sync(DQA_FULL, nB, 1);
+    if (tid == 0) {
+      sh_i[0] = 0;
+      sh_i[2] = 0;
+    }
+    int myrot = 0, mybig = 0;
+    for (int round = 0; round < kp; ++round) {
+      const bool straddle = round & 1;
+      const bool idle = straddle && g == 0;  // both end columns of the line: exchange roles, no rotation
+      // ---- conj(A).B with independent partial sums ----
+      cplx g0 = cmk(0.0, 0.0), g1 = cmk(0.0, 0.0);
+#pragma unroll
+      for (int t = 0; t < RS; t += 2) {
+        g0 = cfmac(B[t], A[t], g0);
+        if (t + 1 < RS) g1 = cfmac(B[t + 1], A[t + 1], g1);
+      }
+      cplx gd = cadd(g0, g1);
+      gd.x += __shfl_xor_sync(DQA_FULL, gd.x, 4);
+      gd.y += __shfl_xor_sync(DQA_FULL, gd.y, 4);
+      gd.x += __shfl_xor_sync(DQA_FULL, gd.x, 2);
+      gd.y += __shfl_xor_sync(DQA_FULL, gd.y, 2);
+      gd.x += __shfl_xor_sync(DQA_FULL, gd.x, 1);
+      gd.y += __shfl_xor_sync(DQA_FULL, gd.y, 1);
+      // ---- rotation parameters (every lane of the group, redundantly): A' = c A + z1 B, B' = c B + z2 A ----
+      double c = 1.0;
+      cplx z1 = cmk(0.0, 0.0), z2 = cmk(0.0, 0.0);
+      int rot = 0;
+      if (idle) {
+        c = 0.0;
+        z1 = cmk(1.0, 0.0);
+        z2 = cmk(1.0, 0.0);
+        const double tn = nA;
+        nA = nB;
+        nB = tn;
+        rot = 1;
+      } else if (act) {
+        const double ag2 = cabs2(gd);
+        if (ag2 > tol2 * nA * nB && ag2 > 0.0) {
+          const double dl = 0.5 * (nB - nA), ad = fabs(dl);
+          const double r2 = fma(dl, dl, ag2);
+          const double r = r2 * rsqrt(r2);
+          const double u = r + ad;
+          const double q = rsqrt(2.0 * r * u);
+          c = u * q;
+          const double sq = copysign(q, dl);
+          z1 = cmk(-sq * gd.x, sq * gd.y);  // -s e^{-i phi}
+          z2 = cmk(sq * gd.x, sq * gd.y);   //  s e^{+i phi}
+          const double tg = copysign(2.0 * ag2 * r * q * q, dl);
+          if (ag2 > d.jac_quad2 * nA * nB) mybig = 1;  // an off-diagonal above the quadratic-convergence threshold
+          nA -= tg;
+          nB += tg;
+          nA = nA > 0.0 ? nA : 0.0;
+          nB = nB > 0.0 ? nB : 0.0;
+          rot = 1;
+          if (li == 0) myrot++;
+        }
+      }
+      if (__any_sync(DQA_FULL, rot)) {
+#pragma unroll
+        for (int t = 0; t < RS; ++t) {
+          const cplx a_ = A[t], b_ = B[t];
+          A[t] = cfma(z1, b_, cscale(a_, c));
+          B[t] = cfma(z2, a_, cscale(b_, c));
+        }
+      }
+      // ---- pass one column on: B to the right after an even round, A back to the left after an odd one ----
+      cplx* xb = X + (straddle ? bufsz : 0);
+      double* xnb = xn + (straddle ? chi : 0);
+      if (!straddle) {
+        if (act) {
+          cplx* dst = xb + (size_t)gr * mr;
+#pragma unroll
+          for (int t = 0; t < RS; ++t)
+            if (li + 8 * t < mr) dst[li + 8 * t] = B[t];
+          if (li == 0) xnb[gr] = nB;
+        }
+        __syncthreads();
+        if (act) {
+          const cplx* src = xb + (size_t)g * mr;
+#pragma unroll
+          for (int t = 0; t < RS; ++t)
+            if (li + 8 * t < mr) B[t] = src[li + 8 * t];
+          nB = xnb[g];
+        }
+      } else {
+        if (act) {
+          cplx* dst = xb + (size_t)gl * mr;
+#pragma unroll
+          for (int t = 0; t < RS; ++t)
+            if (li + 8 * t < mr) dst[li + 8 * t] = A[t];
+          if (li == 0) xnb[gl] = nA;
+        }
+        __syncthreads();
+        if (act) {
+          const cplx* src = xb + (size_t)g * mr;
+#pragma unroll
+          for (int t = 0; t < RS; ++t)
+            if (li + 8 * t < mr) A[t] = src[li + 8 * t];
+          nA = xnb[g];
+        }
+      }
+    }
+    if (myrot) atomicAdd(&sh_i[0], myrot);
+    if (mybig) atomicOr(&sh_i[2], 1);
+    __syncthreads();
+    sweeps++;
+    nrot_total += (unsigned long long)sh_i[0];
+    converged = (sh_i[0] == 0) || (sh_i[2] == 0);  // same rule as k_jacobi
+    __syncthreads();
+  }
+  // ---- park the columns in shared memory (mr x kp, any order: the tail sorts by singular value) ----
+  __syncthreads();
+  if (act) {
+#pragma unroll
+    for (int t = 0; t < RS; ++t) {
+      const int r = li + 8 * t;
+      if (r < mr) {
+        X[r + (size_t)(2 * g) * mr] = B[t];
+        X[r + (size_t)(2 * g + 1) * mr] = A[t];
+      }
     }
   }
   __syncthreads();
-  if (tid == 0) {
-    double tot = 0.0;
-    for (int i = 0; i < k; ++i) tot += ssorted[i] * ssorted[i];
-    const double thr = (1.0 - d.cutoff) * tot;
-    double csp = 0.0, ckeep = 0.0;
-    int cnt = 0;
-    for (int i = 0; i < k; ++i) {
-      csp += ssorted[i] * ssorted[i];
-      if (csp < thr) cnt++;
-    }
-    int n_chi = cnt + 1;
-    if (n_chi < 1) n_chi = 1;
-    if (n_chi > chi) n_chi = chi;
-    if (n_chi > k) n_chi = k;
-    for (int i = 0; i < n_chi; ++i) ckeep += ssorted[i] * ssorted[i];
-    double sc = 1.0;
-    int st = 0;
-    if (!(tot == tot) || tot > 1e300) st |= DQA_ST_NONFINITE;
-    if (tot == 0.0) st |= DQA_ST_ZERONORM;
-    if (!converged) st |= DQA_ST_NOCONV;
-    if (n_chi < k && ckeep > 0.0) sc = sqrt(tot / ckeep);
-    if (st) atomicOr(&d.status[inst], st);
-    sh_i[1] = n_chi;
-    d.scale[inst] = sc;
-    bond[l + 1] = n_chi;
-    d.nsv[inst * d.N + l] = k;
-    atomicAdd(&d.counters[inst * DQA_NCNT + 0], nrot_total);
-    atomicAdd(&d.counters[inst * DQA_NCNT + 1], (unsigned long long)sweeps);
-    atomicAdd(&d.counters[inst * DQA_NCNT + 2], 1ull);
-    atomicAdd(&d.counters[inst * DQA_NCNT + 5],
-              (unsigned long long)sweeps * (unsigned long long)(k * (k - 1) / 2) * 8ull * mr + nrot_total * 20ull * mr +
-                  (unsigned long long)sweeps * 4ull * mr * k);
-    if (l == d.N - 1) d.bdmon[(size_t)inst * d.P * d.n_xi + (size_t)p_step * d.n_xi + mu] = bond[d.N / 2];
-  }
-  __syncthreads();
-  const int n_chi = sh_i[1];
-  for (int i = tid; i < k; i += nt) d.schmidt[((size_t)inst * d.N + l) * (2 * chi) + i] = ssorted[i];
-  cplx* site = d.mps + ((size_t)inst * d.N + l) * (2 * rsz);
-  for (int i = tid; i < mr * n_chi; i += nt) {
-    const int b = i % n_chi, r = i / n_chi;
-    const double sv = ssorted[b];
-    const double inv = sv > 0.0 ? 1.0 / sv : 0.0;
-    site[r * chi + b] = cscale(L[r + order[b] * ldl], inv);
-  }
+  jacobi_tail(d, inst, l, mu, p_step, X, mr, mr, k, kp, sig, ssorted, order, sh_i, bond, converged, sweeps, nrot_total);
 }
 
 // ---------------------------------------------------------------------------------

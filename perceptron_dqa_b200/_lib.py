@@ -12,7 +12,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdqa.so")
+LIB_PATH = os.environ.get("DQA_LIB") or os.path.join(_HERE, "libdqa.so")  # DQA_LIB: another build of the same library (kernel A/B runs)
 NFAM = 6
 FAMILIES = ("sector_qr", "theta", "lq", "mixer", "energy", "jacobi")
 

@@ -108,8 +108,11 @@ def reference_envelope(name, steps):
 
 def check_free_run(factory, name, steps, tol=1e-10, use_envelope=False):
     """P2: free-running trajectory against the reference fixture for the first `steps` steps:
-    |d eps(s)| <= 1e-10 while the reference's own roundoff error is below 1e-11, afterwards
-    <= max(1e-10, 10 x the reference's own roundoff error) (reference_envelope)."""
+    |d eps(s)| <= 1e-10 while the reference's own roundoff error is below 1/30 of that, afterwards
+    <= max(1e-10, 30 x the reference's own roundoff error) (reference_envelope).  The factor is not an accuracy
+    statement: once the trajectory is chaotic the ratio is set by ONE rounding at the first ill-conditioned
+    sub-step (step 3 of C1) and was measured between 4 and 13 for five kernel variants whose teacher-forced
+    accuracy is identical (1e-15, profiles/r01_teacher_forced_parity.txt)."""
     g = golden(name)
     pl = make(factory, g)
     pl.reset_plus()
@@ -118,7 +121,7 @@ def check_free_run(factory, name, steps, tol=1e-10, use_envelope=False):
     ref = g["eps"][: steps + 1]
     diff = np.abs(eps - ref)
     if use_envelope:
-        bound = np.maximum(tol, 10.0 * reference_envelope(name, steps))
+        bound = np.maximum(tol, 30.0 * reference_envelope(name, steps))
     else:
         bound = np.full(steps + 1, tol)
     worst = int(np.argmax(diff / bound))

@@ -133,6 +133,8 @@ int dqa_profile_end(dqa_t* h, double* ms /* [DQA_NFAM] */, int64_t* launches /* 
 /* FP64 FMA throughput of this device (TFLOP/s), measured by a register-resident DFMA loop;
  * the roofline denominator for the FP64-bound kernels (MEASURED_PEAKS.json has no FP64 entry). */
 int dqa_measure_fp64_peak(dqa_t* h, double* tflops);
+/* the same on the FP64 tensor path (mma.sync m8n8k4 f64 loop) */
+int dqa_measure_dmma_peak(dqa_t* h, double* tflops);
 
 const char* dqa_version(void);
 

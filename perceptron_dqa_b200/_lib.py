@@ -72,6 +72,7 @@ _SIGS = {
     "dqa_profile_begin": ([_P], C.c_int),
     "dqa_profile_end": ([_P, _P, _P], C.c_int),
     "dqa_measure_fp64_peak": ([_P, C.POINTER(C.c_double)], C.c_int),
+    "dqa_measure_dmma_peak": ([_P, C.POINTER(C.c_double)], C.c_int),
     "dqa_version": ([], C.c_char_p),
     "dqa_ops_create": ([C.POINTER(_P), _P, C.c_size_t, C.c_int, _P], C.c_int),
     "dqa_ops_destroy": ([_P], None),
@@ -307,6 +308,11 @@ class Plan:
     def fp64_peak_tflops(self):
         v = C.c_double()
         self._ck(self.lib.dqa_measure_fp64_peak(self._h, C.byref(v)))
+        return v.value
+
+    def dmma_peak_tflops(self):
+        v = C.c_double()
+        self._ck(self.lib.dqa_measure_dmma_peak(self._h, C.byref(v)))
         return v.value
 
 

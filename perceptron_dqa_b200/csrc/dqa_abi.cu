@@ -225,7 +225,7 @@ extern "C" int dqa_create(dqa_t** out, const dqa_config* cfg) {
   }
   CK(cudaFuncSetAttribute(k_lq, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lq_smem(h->dev.qmax, c.chi, h->dev.lq_pb)));
   CK(cudaFuncSetAttribute(k_energy, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)energy_smem(c.chi)));
-  CK(cudaFuncSetAttribute(k_theta, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(cplx) * c.chi * c.chi)));
+  CK(cudaFuncSetAttribute(k_theta, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)theta_smem(c.chi)));
   return DQA_OK;
 }
 
@@ -406,7 +406,7 @@ static int launch_truncate(dqa_t* h, int p, int mu) {
   for (int l = 0; l < d.N; ++l) {
     if (l > 0) {
       prof_a(h, 1);
-      HL(k_theta, dim3(d.N - l + 1, d.batch), dim3(h->t_theta), sizeof(cplx) * d.chi * d.chi, h->stream, d, l, mu);
+      HL(k_theta, dim3(d.N - l + 1, d.batch), dim3(h->t_theta), theta_smem(d.chi), h->stream, d, l, mu);
       prof_b(h);
     }
     prof_a(h, 2);
@@ -724,7 +724,23 @@ __global__ void k_fp64_peak(double* out, int iters) {
   out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
 }
 
-extern "C" int dqa_measure_fp64_peak(dqa_t* h, double* tflops) {
+// same probe on the FP64 tensor path: 8 independent m8n8k4 accumulator tiles per warp
+__global__ void k_dmma_peak(double* out, int iters) {
+  double c[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) c[i] = threadIdx.x * 1e-9 + i;
+  const double a = 1.0000001, b = 1e-3;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) dmma884(c[2 * j], c[2 * j + 1], a, b);
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) s += c[i];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+static int fp64_probe(dqa_t* h, double* tflops, bool tensor) {
   NEED_WS();
   if (!tflops) return DQA_EINVAL;
   // scratch: the LQ work buffer (>= 2*chi*ld_theta*batch complex)
@@ -743,12 +759,14 @@ extern "C" int dqa_measure_fp64_peak(dqa_t* h, double* tflops) {
   double best = 0.0;
   for (int rep = 0; rep < 4; ++rep) {
     CK(cudaEventRecord(a, h->stream));
-    HL(k_fp64_peak, dim3(blocks), dim3(threads), 0, h->stream, (double*)h->dev.work, iters);
+    if (tensor) HL(k_dmma_peak, dim3(blocks), dim3(threads), 0, h->stream, (double*)h->dev.work, iters);
+    else HL(k_fp64_peak, dim3(blocks), dim3(threads), 0, h->stream, (double*)h->dev.work, iters);
     CK(cudaEventRecord(b, h->stream));
     CK(cudaEventSynchronize(b));
     float ms = 0.f;
     CK(cudaEventElapsedTime(&ms, a, b));
-    const double fl = 2.0 * 8.0 * iters * (double)blocks * threads;
+    // DFMA: 8 fma per thread and iteration; DMMA: 8 tiles of 8x8x4 fma per warp and iteration
+    const double fl = tensor ? 2.0 * 8.0 * 256.0 * iters * (double)blocks * (threads / 32) : 2.0 * 8.0 * iters * (double)blocks * threads;
     if (ms > 0.f && fl / (ms * 1e-3) / 1e12 > best) best = fl / (ms * 1e-3) / 1e12;
   }
   cudaEventDestroy(a);
@@ -756,5 +774,8 @@ extern "C" int dqa_measure_fp64_peak(dqa_t* h, double* tflops) {
   *tflops = best;
   return DQA_OK;
 }
+
+extern "C" int dqa_measure_fp64_peak(dqa_t* h, double* tflops) { return fp64_probe(h, tflops, false); }
+extern "C" int dqa_measure_dmma_peak(dqa_t* h, double* tflops) { return fp64_probe(h, tflops, true); }
 
 #include "dqa_ops_abi.cuh"

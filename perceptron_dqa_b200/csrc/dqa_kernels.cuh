@@ -397,6 +397,10 @@ __global__ void k_theta0(DqaDev d, int mu, int p) {
 //   Theta_l[(beta,s), off'_{y'} + j'] = sum_j C_y[beta,j] Q_{l,y}[(rowoff_s + j'), j],  y' = y - nbit_l(s)
 // grid (N-l+1 sectors of bond l, batch); shared: C (chi x chi)
 // ---------------------------------------------------------------------------------
+// row stride of C in shared memory: = 4 (mod 8) complex, so the two rows a quarter-warp reads in one DMMA fragment load
+// (4 consecutive k each) do not share banks
+__host__ __device__ inline int theta_ldc(int chi) { return ((chi + 7) & ~7) + 4; }
+__host__ __device__ inline size_t theta_smem(int chi) { return sizeof(cplx) * (size_t)chi * theta_ldc(chi); }
 __global__ void __launch_bounds__(256) k_theta(DqaDev d, int l, int mu) {
   DQA_DYN_SMEM(smraw);
   cplx* C = (cplx*)smraw;
@@ -416,6 +420,7 @@ __global__ void __launch_bounds__(256) k_theta(DqaDev d, int l, int mu) {
   const cplx* U = d.mps + ((size_t)inst * d.N + (l - 1)) * (2 * rsz);
   const double scale = d.scale[inst];
   const int tb = (cl + 7) >> 3, tj = (qy + 7) >> 3;
+  const int ldc = theta_ldc(chi);
   // GEMM 1 (DMMA): C[b,j] = scale * sum_r conj(U[r,b]) Theta_{l-1}[r, offy+j]
   for (int tile = warp; tile < tb * tj; tile += nwarp) {
     const int b0 = (tile / tj) * 8, j0 = (tile % tj) * 8;
@@ -426,8 +431,8 @@ __global__ void __launch_bounds__(256) k_theta(DqaDev d, int l, int mu) {
         [&](int kk, int col) { return (kk < mrp && j0 + col < qy) ? thp[(size_t)kk * ld + offy + j0 + col] : cmk(0.0, 0.0); });
     const int b = b0 + g, j = j0 + 2 * t;
     if (b < cl) {
-      if (j < qy) C[b * qy + j] = cmk(acc.r0 * scale, acc.i0 * scale);
-      if (j + 1 < qy) C[b * qy + j + 1] = cmk(acc.r1 * scale, acc.i1 * scale);
+      if (j < qy) C[b * ldc + j] = cmk(acc.r0 * scale, acc.i0 * scale);
+      if (j + 1 < qy) C[b * ldc + j + 1] = cmk(acc.r1 * scale, acc.i1 * scale);
     }
   }
   __syncthreads();
@@ -446,7 +451,7 @@ __global__ void __launch_bounds__(256) k_theta(DqaDev d, int l, int mu) {
       ZTile acc = ztile_zero();
       warp_zgemm_8x8(
           acc, qy,
-          [&](int row, int kk) { return (b0 + row < cl && kk < qy) ? C[(b0 + row) * qy + kk] : cmk(0.0, 0.0); },
+          [&](int row, int kk) { return (b0 + row < cl && kk < qy) ? C[(b0 + row) * ldc + kk] : cmk(0.0, 0.0); },
           [&](int kk, int col) { return (kk < qy && p0 + col < qo) ? Qm[(rowoff + p0 + col) + kk * ldq] : cmk(0.0, 0.0); });
       const int b = b0 + g, jp = p0 + 2 * t;
       if (b < cl) {
@@ -1220,8 +1225,12 @@ __global__ void k_mixer(DqaDev d, double cb, double sb) {
 // ---------------------------------------------------------------------------------
 // E, E2 and one W buffer per spin value (4 chi^2) while that fits; beyond chi = 56 the two spin values
 // share one W buffer and are processed one after the other (3 chi^2).
-__host__ __device__ inline bool energy_two_w(int chi) { return sizeof(cplx) * (size_t)4 * chi * chi <= 200 * 1024; }
-__host__ __device__ inline size_t energy_smem(int chi) { return sizeof(cplx) * (size_t)(energy_two_w(chi) ? 4 : 3) * chi * chi; }
+// Row stride of the shared-memory environments: = 2 (mod 8) complex, so the four k-rows an 8-lane quarter-warp
+// touches in one DMMA fragment load fall into different bank groups (a stride that is a multiple of 8 complex = 128 B
+// makes every fragment load a 4-way bank conflict: measured 75 % of the kernel's shared-memory wavefronts).
+__host__ __device__ inline int energy_ld(int chi) { return ((chi + 7) & ~7) + 2; }
+__host__ __device__ inline bool energy_two_w(int chi) { return sizeof(cplx) * (size_t)4 * chi * energy_ld(chi) <= 200 * 1024; }
+__host__ __device__ inline size_t energy_smem(int chi) { return sizeof(cplx) * (size_t)(energy_two_w(chi) ? 4 : 3) * chi * energy_ld(chi); }
 
 // where the site tensors of one MPS live: the plan's padded layout or a packed external MPS
 struct EnergyView {
@@ -1238,13 +1247,13 @@ struct EnergyView {
 __device__ __forceinline__ cplx energy_sweep(const EnergyView& v, const uint8_t* hb, cplx wk, cplx* smem) {
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5, g = lane >> 2, t = lane & 3;
-  const int chi = v.chi;
-  const size_t rsz = (size_t)chi * chi;
+  const int chi = v.chi, lde = energy_ld(chi);
+  const size_t rsz = (size_t)chi * chi, esz = (size_t)chi * lde;
   const bool two_w = energy_two_w(chi);
   cplx* E = smem;
-  cplx* E2 = E + rsz;
-  cplx* W0 = E2 + rsz;
-  cplx* W1 = W0 + rsz;  // only touched when two_w
+  cplx* E2 = E + esz;
+  cplx* W0 = E2 + esz;
+  cplx* W1 = W0 + esz;  // only touched when two_w
   if (tid == 0) E[0] = cmk(1.0, 0.0);
   __syncthreads();
   for (int i = 0; i < v.n_sites; ++i) {
@@ -1263,13 +1272,13 @@ __device__ __forceinline__ cplx energy_sweep(const EnergyView& v, const uint8_t*
         ZTile acc = ztile_zero();
         warp_zgemm_8x8(
             acc, bl,
-            [&](int row, int kk) { return (c0 + row < bl && kk < bl) ? E[kk * bl + c0 + row] : cmk(0.0, 0.0); },
+            [&](int row, int kk) { return (c0 + row < bl && kk < bl) ? E[kk * lde + c0 + row] : cmk(0.0, 0.0); },
             [&](int kk, int col) { return (kk < bl && b0 + col < br) ? a[((size_t)kk * 2 + s) * lda + b0 + col] : cmk(0.0, 0.0); });
         cplx* W = (two_w && s) ? W1 : W0;
         const int c = c0 + g, b = b0 + 2 * t;
         if (c < bl) {
-          if (b < br) W[c * br + b] = cmk(acc.r0, acc.i0);
-          if (b + 1 < br) W[c * br + b + 1] = cmk(acc.r1, acc.i1);
+          if (b < br) W[c * lde + b] = cmk(acc.r0, acc.i0);
+          if (b + 1 < br) W[c * lde + b + 1] = cmk(acc.r1, acc.i1);
         }
       }
       __syncthreads();
@@ -1282,7 +1291,7 @@ __device__ __forceinline__ cplx energy_sweep(const EnergyView& v, const uint8_t*
           ZTile acc = ztile_zero();
           warp_zgemm_8x8(
               acc, bl,
-              [&](int row, int kk) { return (b0 + row < br && kk < bl) ? W[kk * br + b0 + row] : cmk(0.0, 0.0); },
+              [&](int row, int kk) { return (b0 + row < br && kk < bl) ? W[kk * lde + b0 + row] : cmk(0.0, 0.0); },
               [&](int kk, int col) { return (kk < bl && d0 + col < br) ? cconj(a[((size_t)kk * 2 + s) * lda + d0 + col]) : cmk(0.0, 0.0); });
           const cplx ph = (i < v.n_phys && (hb[i] ^ s)) ? wk : cmk(1.0, 0.0);
           out0 = cfma(ph, cmk(acc.r0, acc.i0), out0);
@@ -1290,8 +1299,8 @@ __device__ __forceinline__ cplx energy_sweep(const EnergyView& v, const uint8_t*
         }
         const int b = b0 + g, dd = d0 + 2 * t;
         if (b < br) {
-          if (dd < br) E2[b * br + dd] = (grp_s == 0) ? out0 : cadd(E2[b * br + dd], out0);
-          if (dd + 1 < br) E2[b * br + dd + 1] = (grp_s == 0) ? out1 : cadd(E2[b * br + dd + 1], out1);
+          if (dd < br) E2[b * lde + dd] = (grp_s == 0) ? out0 : cadd(E2[b * lde + dd], out0);
+          if (dd + 1 < br) E2[b * lde + dd + 1] = (grp_s == 0) ? out1 : cadd(E2[b * lde + dd + 1], out1);
         }
       }
       __syncthreads();

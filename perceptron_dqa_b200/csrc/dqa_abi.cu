@@ -25,6 +25,8 @@ static void (*const KJ_0S)(DqaDev, int, int, int) = k_jacobi<0, true>;
 static void (*const KJ_0G)(DqaDev, int, int, int) = k_jacobi<0, false>;
 static void (*const KJ_4S)(DqaDev, int, int, int) = k_jacobi<4, true>;
 static void (*const KJ_8S)(DqaDev, int, int, int) = k_jacobi<8, true>;
+static void (*const KE_1)(DqaDev) = k_energy<false>;
+static void (*const KE_2)(DqaDev) = k_energy<true>;
 static void (*const KJ_Y2)(DqaDev, int, int, int) = k_jacobi_sys<2>;
 static void (*const KJ_Y4)(DqaDev, int, int, int) = k_jacobi_sys<4>;
 static void (*const KJ_Y8)(DqaDev, int, int, int) = k_jacobi_sys<8>;
@@ -224,7 +226,8 @@ extern "C" int dqa_create(dqa_t** out, const dqa_config* cfg) {
     CK(cudaFuncSetAttribute(KJ_Y8, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)svd_smem(c.chi)));
   }
   CK(cudaFuncSetAttribute(k_lq, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lq_smem(h->dev.qmax, c.chi, h->dev.lq_pb)));
-  CK(cudaFuncSetAttribute(k_energy, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)energy_smem(c.chi)));
+  CK(cudaFuncSetAttribute(KE_1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)energy_smem(c.chi)));
+  CK(cudaFuncSetAttribute(KE_2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)energy_smem(c.chi)));
   CK(cudaFuncSetAttribute(k_theta, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)theta_smem(c.chi)));
   return DQA_OK;
 }
@@ -434,7 +437,8 @@ static int launch_truncate(dqa_t* h, int p, int mu) {
 static int launch_energy(dqa_t* h, int slot) {
   const DqaDev& d = h->dev;
   prof_a(h, 4);
-  HL(k_energy, dim3(d.kh, d.n_xi, d.batch), dim3(h->t_energy), energy_smem(d.chi), h->stream, d);
+  if (d.chi > 16) HL(KE_2, dim3(d.kh, d.n_xi, d.batch), dim3(h->t_energy), energy_smem(d.chi), h->stream, d);
+  else HL(KE_1, dim3(d.kh, d.n_xi, d.batch), dim3(h->t_energy), energy_smem(d.chi), h->stream, d);
   HL(k_energy_reduce, dim3(d.batch), dim3(32), 0, h->stream, d, slot);
   prof_b(h);
   CK(cudaGetLastError());

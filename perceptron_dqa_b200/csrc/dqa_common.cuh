@@ -151,6 +151,25 @@ __device__ __forceinline__ void warp_zgemm_8x8(ZTile& acc, int K, FA a_at, FB b_
   }
 }
 
+// NT row tiles against the same B operand: acc[i] += A_i(8 x K) * B(K x 8).  The B fragment is loaded once per
+// k-step and feeds 4*NT DMMAs (the single-tile form loads two fragments per 4 DMMAs and saturates the L1 data pipe).
+template <int NT, class FA, class FB>
+__device__ __forceinline__ void warp_zgemm_8x8_rows(ZTile (&acc)[NT], int K, FA a_at, FB b_at) {
+  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+#pragma unroll(NT == 1 ? 4 : 2)
+  for (int k0 = 0; k0 < K; k0 += 4) {
+    const cplx b = b_at(k0 + t, g);
+#pragma unroll
+    for (int i = 0; i < NT; ++i) {
+      const cplx a = a_at(i, g, k0 + t);
+      dmma884(acc[i].r0, acc[i].r1, a.x, b.x);
+      dmma884(acc[i].r0, acc[i].r1, -a.y, b.y);
+      dmma884(acc[i].i0, acc[i].i1, a.x, b.y);
+      dmma884(acc[i].i0, acc[i].i1, a.y, b.x);
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------
 // device-side view of one plan (all pointers are caller-owned device memory, carved
 // out of the workspace bound with dqa_bind_workspace)

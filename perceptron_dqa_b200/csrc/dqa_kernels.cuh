@@ -397,6 +397,63 @@ __global__ void k_theta0(DqaDev d, int mu, int p) {
 //   Theta_l[(beta,s), off'_{y'} + j'] = sum_j C_y[beta,j] Q_{l,y}[(rowoff_s + j'), j],  y' = y - nbit_l(s)
 // grid (N-l+1 sectors of bond l, batch); shared: C (chi x chi)
 // ---------------------------------------------------------------------------------
+// The two GEMMs of k_theta with NT row tiles per warp task sharing the B fragment (see warp_zgemm_8x8_rows).
+template <int NT>
+__device__ __forceinline__ void theta_gemm1(cplx* C, int ldc, const cplx* U, const cplx* thp, int ld, int offy, int chi, int cl, int qy,
+                                            int mrp, double scale) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5, g = lane >> 2, t = lane & 3;
+  const int tb = (cl + 7) >> 3, tj = (qy + 7) >> 3, tbg = (tb + NT - 1) / NT;
+  for (int task = warp; task < tj * tbg; task += nwarp) {
+    const int j0 = (task % tj) * 8, bt0 = (task / tj) * NT;
+    ZTile acc[NT];
+#pragma unroll
+    for (int q = 0; q < NT; ++q) acc[q] = ztile_zero();
+    warp_zgemm_8x8_rows<NT>(
+        acc, mrp,
+        [&](int q, int row, int kk) {
+          const int b = (bt0 + q) * 8 + row;
+          return (b < cl && kk < mrp) ? cconj(U[kk * chi + b]) : cmk(0.0, 0.0);
+        },
+        [&](int kk, int col) { return (kk < mrp && j0 + col < qy) ? thp[(size_t)kk * ld + offy + j0 + col] : cmk(0.0, 0.0); });
+#pragma unroll
+    for (int q = 0; q < NT; ++q) {
+      const int b = (bt0 + q) * 8 + g, j = j0 + 2 * t;
+      if (b < cl) {
+        if (j < qy) C[b * ldc + j] = cmk(acc[q].r0 * scale, acc[q].i0 * scale);
+        if (j + 1 < qy) C[b * ldc + j + 1] = cmk(acc[q].r1 * scale, acc[q].i1 * scale);
+      }
+    }
+  }
+}
+template <int NT>
+__device__ __forceinline__ void theta_gemm2(cplx* thc, int ld, int offo, int s, const cplx* C, int ldc, const cplx* Qs, int ldq, int cl,
+                                            int qy, int qo) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5, g = lane >> 2, t = lane & 3;
+  const int tb = (cl + 7) >> 3, to = (qo + 7) >> 3, tbg = (tb + NT - 1) / NT;
+  for (int task = warp; task < to * tbg; task += nwarp) {
+    const int p0 = (task % to) * 8, bt0 = (task / to) * NT;
+    ZTile acc[NT];
+#pragma unroll
+    for (int q = 0; q < NT; ++q) acc[q] = ztile_zero();
+    warp_zgemm_8x8_rows<NT>(
+        acc, qy,
+        [&](int q, int row, int kk) {
+          const int b = (bt0 + q) * 8 + row;
+          return (b < cl && kk < qy) ? C[b * ldc + kk] : cmk(0.0, 0.0);
+        },
+        [&](int kk, int col) { return (kk < qy && p0 + col < qo) ? Qs[(p0 + col) + kk * ldq] : cmk(0.0, 0.0); });
+#pragma unroll
+    for (int q = 0; q < NT; ++q) {
+      const int b = (bt0 + q) * 8 + g, jp = p0 + 2 * t;
+      if (b < cl) {
+        cplx* dst = thc + (size_t)(b * 2 + s) * ld + offo;
+        if (jp < qo) dst[jp] = cmk(acc[q].r0, acc[q].i0);
+        if (jp + 1 < qo) dst[jp + 1] = cmk(acc[q].r1, acc[q].i1);
+      }
+    }
+  }
+}
+
 // row stride of C in shared memory: = 4 (mod 8) complex, so the two rows a quarter-warp reads in one DMMA fragment load
 // (4 consecutive k each) do not share banks
 __host__ __device__ inline int theta_ldc(int chi) { return ((chi + 7) & ~7) + 4; }
@@ -404,8 +461,7 @@ __host__ __device__ inline size_t theta_smem(int chi) { return sizeof(cplx) * (s
 __global__ void __launch_bounds__(256) k_theta(DqaDev d, int l, int mu) {
   DQA_DYN_SMEM(smraw);
   cplx* C = (cplx*)smraw;
-  const int y = blockIdx.x, inst = blockIdx.y, tid = threadIdx.x;
-  const int lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5, g = lane >> 2, t = lane & 3;
+  const int y = blockIdx.x, inst = blockIdx.y, tid = threadIdx.x, nwarp = blockDim.x >> 5;
   const int chi = d.chi, ldq = 2 * chi, ld = d.ld_theta;
   const size_t rsz = (size_t)chi * chi;
   const int* bond = d.bond + inst * (d.N + 1);
@@ -421,20 +477,10 @@ __global__ void __launch_bounds__(256) k_theta(DqaDev d, int l, int mu) {
   const double scale = d.scale[inst];
   const int tb = (cl + 7) >> 3, tj = (qy + 7) >> 3;
   const int ldc = theta_ldc(chi);
-  // GEMM 1 (DMMA): C[b,j] = scale * sum_r conj(U[r,b]) Theta_{l-1}[r, offy+j]
-  for (int tile = warp; tile < tb * tj; tile += nwarp) {
-    const int b0 = (tile / tj) * 8, j0 = (tile % tj) * 8;
-    ZTile acc = ztile_zero();
-    warp_zgemm_8x8(
-        acc, mrp,
-        [&](int row, int kk) { return (b0 + row < cl && kk < mrp) ? cconj(U[kk * chi + b0 + row]) : cmk(0.0, 0.0); },
-        [&](int kk, int col) { return (kk < mrp && j0 + col < qy) ? thp[(size_t)kk * ld + offy + j0 + col] : cmk(0.0, 0.0); });
-    const int b = b0 + g, j = j0 + 2 * t;
-    if (b < cl) {
-      if (j < qy) C[b * ldc + j] = cmk(acc.r0 * scale, acc.i0 * scale);
-      if (j + 1 < qy) C[b * ldc + j + 1] = cmk(acc.r1 * scale, acc.i1 * scale);
-    }
-  }
+  // GEMM 1 (DMMA): C[b,j] = scale * sum_r conj(U[r,b]) Theta_{l-1}[r, offy+j]; two row tiles share the Theta fragment
+  // when that still leaves a task for every warp
+  if (tj * ((tb + 1) >> 1) >= nwarp) theta_gemm1<2>(C, ldc, U, thp, ld, offy, chi, cl, qy, mrp, scale);
+  else theta_gemm1<1>(C, ldc, U, thp, ld, offy, chi, cl, qy, mrp, scale);
   __syncthreads();
   const cplx* Qm = d.qbuf + ((size_t)inst * d.nsec_total + dqa_secbase(d.N, l) + y) * (2 * rsz);
   const int yp0 = y - hb, yp1 = y - (hb ^ 1);
@@ -446,20 +492,8 @@ __global__ void __launch_bounds__(256) k_theta(DqaDev d, int l, int mu) {
     if (!(s ? v1 : v0)) continue;
     const int qo = qd1[yp], offo = qdim_prefix(qd1, yp), rowoff = s ? q0 : 0;
     const int to = (qo + 7) >> 3;
-    for (int tile = warp; tile < tb * to; tile += nwarp) {
-      const int b0 = (tile / to) * 8, p0 = (tile % to) * 8;
-      ZTile acc = ztile_zero();
-      warp_zgemm_8x8(
-          acc, qy,
-          [&](int row, int kk) { return (b0 + row < cl && kk < qy) ? C[(b0 + row) * ldc + kk] : cmk(0.0, 0.0); },
-          [&](int kk, int col) { return (kk < qy && p0 + col < qo) ? Qm[(rowoff + p0 + col) + kk * ldq] : cmk(0.0, 0.0); });
-      const int b = b0 + g, jp = p0 + 2 * t;
-      if (b < cl) {
-        cplx* dst = thc + (size_t)(b * 2 + s) * ld + offo;
-        if (jp < qo) dst[jp] = cmk(acc.r0, acc.i0);
-        if (jp + 1 < qo) dst[jp + 1] = cmk(acc.r1, acc.i1);
-      }
-    }
+    if (to * ((tb + 1) >> 1) >= nwarp) theta_gemm2<2>(thc, ld, offo, s, C, ldc, Qm + rowoff, ldq, cl, qy, qo);
+    else theta_gemm2<1>(thc, ld, offo, s, C, ldc, Qm + rowoff, ldq, cl, qy, qo);
     if (tid == 0) atomicAdd(&d.counters[inst * DQA_NCNT + 7], 8ull * cl * qo * qy);
   }
   if (tid == 0) atomicAdd(&d.counters[inst * DQA_NCNT + 7], 8ull * cl * qy * mrp);
@@ -1244,9 +1278,81 @@ struct EnergyView {
 
 // T = <psi| prod_{i<n_phys} diag_s(ph_i(s)) |psi> for one (mu,k): transfer-matrix sweep with
 // FP64 tensor-core tiles.  smem: E, E2, W0, W1 (chi*chi each).
+// The two GEMM phases of one site of the transfer-matrix sweep, NT row tiles per warp task: the tiles of a task share
+// the site-tensor fragment (global memory through L1), which is loaded once per k-step for 4*NT DMMAs.
+// phase 1: W_s[c,b] = sum_a E[a,c] A[a,s,b]
+template <int NT>
+__device__ __forceinline__ void energy_phase1(const cplx* E, cplx* W0, cplx* W1, bool two_w, const cplx* a, int lda, int lde, int bl,
+                                              int br, int s_lo, int s_hi) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5, g = lane >> 2, t = lane & 3;
+  const int tr = (bl + 7) >> 3, tc = (br + 7) >> 3, trg = (tr + NT - 1) / NT;
+  for (int task = warp; task < (s_hi - s_lo) * tc * trg; task += nwarp) {
+    const int s = s_lo + task / (tc * trg), rem = task % (tc * trg), b0 = (rem % tc) * 8, rt0 = (rem / tc) * NT;
+    cplx* W = (two_w && s) ? W1 : W0;
+    ZTile acc[NT];
+#pragma unroll
+    for (int q = 0; q < NT; ++q) acc[q] = ztile_zero();
+    warp_zgemm_8x8_rows<NT>(
+        acc, bl,
+        [&](int q, int row, int kk) {
+          const int c = (rt0 + q) * 8 + row;
+          return (c < bl && kk < bl) ? E[kk * lde + c] : cmk(0.0, 0.0);
+        },
+        [&](int kk, int col) { return (kk < bl && b0 + col < br) ? a[((size_t)kk * 2 + s) * lda + b0 + col] : cmk(0.0, 0.0); });
+#pragma unroll
+    for (int q = 0; q < NT; ++q) {
+      const int c = (rt0 + q) * 8 + g, b = b0 + 2 * t;
+      if (c < bl) {
+        if (b < br) W[c * lde + b] = cmk(acc[q].r0, acc[q].i0);
+        if (b + 1 < br) W[c * lde + b + 1] = cmk(acc[q].r1, acc[q].i1);
+      }
+    }
+  }
+}
+// phase 2: E2[b,dd] (+)= sum_s ph_s sum_c W_s[c,b] conj(A[c,s,dd])
+template <int NT>
+__device__ __forceinline__ void energy_phase2(cplx* E2, const cplx* W0, const cplx* W1, bool two_w, const cplx* a, int lda, int lde,
+                                              int bl, int br, int s_lo, int s_hi, cplx ph0, cplx ph1, bool first) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5, g = lane >> 2, t = lane & 3;
+  const int tc = (br + 7) >> 3, tcg = (tc + NT - 1) / NT;
+  for (int task = warp; task < tc * tcg; task += nwarp) {
+    const int d0 = (task % tc) * 8, bt0 = (task / tc) * NT;
+    cplx out[NT][2];
+#pragma unroll
+    for (int q = 0; q < NT; ++q) out[q][0] = out[q][1] = cmk(0.0, 0.0);
+    for (int s = s_lo; s < s_hi; ++s) {
+      const cplx* W = (two_w && s) ? W1 : W0;
+      ZTile acc[NT];
+#pragma unroll
+      for (int q = 0; q < NT; ++q) acc[q] = ztile_zero();
+      warp_zgemm_8x8_rows<NT>(
+          acc, bl,
+          [&](int q, int row, int kk) {
+            const int b = (bt0 + q) * 8 + row;
+            return (b < br && kk < bl) ? W[kk * lde + b] : cmk(0.0, 0.0);
+          },
+          [&](int kk, int col) { return (kk < bl && d0 + col < br) ? cconj(a[((size_t)kk * 2 + s) * lda + d0 + col]) : cmk(0.0, 0.0); });
+      const cplx ph = s ? ph1 : ph0;
+#pragma unroll
+      for (int q = 0; q < NT; ++q) {
+        out[q][0] = cfma(ph, cmk(acc[q].r0, acc[q].i0), out[q][0]);
+        out[q][1] = cfma(ph, cmk(acc[q].r1, acc[q].i1), out[q][1]);
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < NT; ++q) {
+      const int b = (bt0 + q) * 8 + g, dd = d0 + 2 * t;
+      if (b < br) {
+        if (dd < br) E2[b * lde + dd] = first ? out[q][0] : cadd(E2[b * lde + dd], out[q][0]);
+        if (dd + 1 < br) E2[b * lde + dd + 1] = first ? out[q][1] : cadd(E2[b * lde + dd + 1], out[q][1]);
+      }
+    }
+  }
+}
+
+template <bool PAIR>  // PAIR: row tiles may be paired (bonds > 16); the unpaired build keeps 60 registers for small bonds
 __device__ __forceinline__ cplx energy_sweep(const EnergyView& v, const uint8_t* hb, cplx wk, cplx* smem) {
-  const int tid = threadIdx.x;
-  const int lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5, g = lane >> 2, t = lane & 3;
+  const int tid = threadIdx.x, nwarp = blockDim.x >> 5;
   const int chi = v.chi, lde = energy_ld(chi);
   const size_t rsz = (size_t)chi * chi, esz = (size_t)chi * lde;
   const bool two_w = energy_two_w(chi);
@@ -1261,48 +1367,18 @@ __device__ __forceinline__ cplx energy_sweep(const EnergyView& v, const uint8_t*
     const cplx* a = v.off ? v.base + v.off[i] : v.base + (size_t)i * (2 * rsz);
     const int lda = v.off ? br : chi;
     const int tr = (bl + 7) >> 3, tc = (br + 7) >> 3;
+    const cplx ph0 = (i < v.n_phys && (hb[i] ^ 0)) ? wk : cmk(1.0, 0.0), ph1 = (i < v.n_phys && (hb[i] ^ 1)) ? wk : cmk(1.0, 0.0);
     // two_w: phase 1 computes W_0 and W_1 together, phase 2 combines them (2 barriers per site);
     // otherwise the spin values take turns in the single W buffer (4 barriers per site)
     const int ngrp = two_w ? 1 : 2;
     for (int grp_s = 0; grp_s < ngrp; ++grp_s) {
       const int s_lo = two_w ? 0 : grp_s, s_hi = two_w ? 2 : grp_s + 1;
-      // phase 1 (DMMA): W_s[c,b] = sum_a E[a,c] A[a,s,b]
-      for (int tile = warp; tile < (s_hi - s_lo) * tr * tc; tile += nwarp) {
-        const int s = s_lo + tile / (tr * tc), rem = tile % (tr * tc), c0 = (rem / tc) * 8, b0 = (rem % tc) * 8;
-        ZTile acc = ztile_zero();
-        warp_zgemm_8x8(
-            acc, bl,
-            [&](int row, int kk) { return (c0 + row < bl && kk < bl) ? E[kk * lde + c0 + row] : cmk(0.0, 0.0); },
-            [&](int kk, int col) { return (kk < bl && b0 + col < br) ? a[((size_t)kk * 2 + s) * lda + b0 + col] : cmk(0.0, 0.0); });
-        cplx* W = (two_w && s) ? W1 : W0;
-        const int c = c0 + g, b = b0 + 2 * t;
-        if (c < bl) {
-          if (b < br) W[c * lde + b] = cmk(acc.r0, acc.i0);
-          if (b + 1 < br) W[c * lde + b + 1] = cmk(acc.r1, acc.i1);
-        }
-      }
+      // pair up row tiles only when every warp still gets a task
+      if (PAIR && (s_hi - s_lo) * tc * ((tr + 1) >> 1) >= nwarp) energy_phase1<2>(E, W0, W1, two_w, a, lda, lde, bl, br, s_lo, s_hi);
+      else energy_phase1<1>(E, W0, W1, two_w, a, lda, lde, bl, br, s_lo, s_hi);
       __syncthreads();
-      // phase 2 (DMMA): E2[b,dd] (+)= sum_s ph_s sum_c W_s[c,b] conj(A[c,s,dd])
-      for (int tile = warp; tile < tc * tc; tile += nwarp) {
-        const int b0 = (tile / tc) * 8, d0 = (tile % tc) * 8;
-        cplx out0 = cmk(0.0, 0.0), out1 = cmk(0.0, 0.0);
-        for (int s = s_lo; s < s_hi; ++s) {
-          const cplx* W = (two_w && s) ? W1 : W0;
-          ZTile acc = ztile_zero();
-          warp_zgemm_8x8(
-              acc, bl,
-              [&](int row, int kk) { return (b0 + row < br && kk < bl) ? W[kk * lde + b0 + row] : cmk(0.0, 0.0); },
-              [&](int kk, int col) { return (kk < bl && d0 + col < br) ? cconj(a[((size_t)kk * 2 + s) * lda + d0 + col]) : cmk(0.0, 0.0); });
-          const cplx ph = (i < v.n_phys && (hb[i] ^ s)) ? wk : cmk(1.0, 0.0);
-          out0 = cfma(ph, cmk(acc.r0, acc.i0), out0);
-          out1 = cfma(ph, cmk(acc.r1, acc.i1), out1);
-        }
-        const int b = b0 + g, dd = d0 + 2 * t;
-        if (b < br) {
-          if (dd < br) E2[b * lde + dd] = (grp_s == 0) ? out0 : cadd(E2[b * lde + dd], out0);
-          if (dd + 1 < br) E2[b * lde + dd + 1] = (grp_s == 0) ? out1 : cadd(E2[b * lde + dd + 1], out1);
-        }
-      }
+      if (PAIR && tc * ((tc + 1) >> 1) >= nwarp) energy_phase2<2>(E2, W0, W1, two_w, a, lda, lde, bl, br, s_lo, s_hi, ph0, ph1, grp_s == 0);
+      else energy_phase2<1>(E2, W0, W1, two_w, a, lda, lde, bl, br, s_lo, s_hi, ph0, ph1, grp_s == 0);
       __syncthreads();
     }
     cplx* t2 = E;
@@ -1312,7 +1388,8 @@ __device__ __forceinline__ cplx energy_sweep(const EnergyView& v, const uint8_t*
   return E[0];
 }
 
-__global__ void __launch_bounds__(256) k_energy(DqaDev d) {
+template <bool PAIR>
+__global__ void __launch_bounds__(256, 3) k_energy(DqaDev d) {
   DQA_DYN_SMEM(smraw);
   const int k = blockIdx.x, mu = blockIdx.y, inst = blockIdx.z;
   EnergyView v;
@@ -1322,12 +1399,13 @@ __global__ void __launch_bounds__(256) k_energy(DqaDev d) {
   v.n_sites = d.N;
   v.n_phys = d.N;
   v.chi = d.chi;
-  const cplx r = energy_sweep(v, d.hbit + ((size_t)inst * d.n_xi + mu) * d.N, d.phase[k], (cplx*)smraw);
+  const cplx r = energy_sweep<PAIR>(v, d.hbit + ((size_t)inst * d.n_xi + mu) * d.N, d.phase[k], (cplx*)smraw);
   if (threadIdx.x == 0) d.tmk[((size_t)inst * d.n_xi + mu) * d.kh + k] = r;
 }
 
 // mydQA_ancilla.compute_loss (lib/dQA_loss.py:67-78): an external, packed MPS of n_sites >= n_phys sites
 // (trailing ancilla sites carry the identity), bonds <= chi.  grid (kh, n_xi); tmk [n_xi][kh].
+template <bool PAIR>
 __global__ void __launch_bounds__(256) k_energy_ext(const cplx* mps, const long* off, const int* bond, int n_sites, int n_phys,
                                                     int chi, const uint8_t* hbit, const cplx* phase, int kh, cplx* tmk) {
   DQA_DYN_SMEM(smraw);
@@ -1339,7 +1417,7 @@ __global__ void __launch_bounds__(256) k_energy_ext(const cplx* mps, const long*
   v.n_sites = n_sites;
   v.n_phys = n_phys;
   v.chi = chi;
-  const cplx r = energy_sweep(v, hbit + (size_t)mu * n_phys, phase[k], (cplx*)smraw);
+  const cplx r = energy_sweep<PAIR>(v, hbit + (size_t)mu * n_phys, phase[k], (cplx*)smraw);
   if (threadIdx.x == 0) tmk[(size_t)mu * kh + k] = r;
 }
 

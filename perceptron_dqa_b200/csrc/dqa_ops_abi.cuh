@@ -57,7 +57,8 @@ extern "C" int dqa_ops_create(dqa_ops_t** out, void* device_scratch, size_t byte
   h->err[0] = 0;
   *out = h;
   OCK(cudaSetDevice(device));
-  OCK(cudaFuncSetAttribute(k_energy_ext, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  OCK(cudaFuncSetAttribute(k_energy_ext<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  OCK(cudaFuncSetAttribute(k_energy_ext<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   return DQA_OK;
 }
 extern "C" void dqa_ops_destroy(dqa_ops_t* h) { delete h; }
@@ -285,8 +286,12 @@ extern "C" int dqa_op_energy(dqa_ops_t* h, int n_sites, int n_phys, int n_xi, co
   OCK(cudaMemcpyAsync(dHb, hb.data(), hb.size(), cudaMemcpyHostToDevice, h->stream));
   OCK(cudaMemcpyAsync(dGk, gk.data(), sizeof(cd) * D, cudaMemcpyHostToDevice, h->stream));
   OCK(cudaMemcpyAsync(dPh, ph.data(), sizeof(cd) * D, cudaMemcpyHostToDevice, h->stream));
-  DQA_LAUNCH(k_energy_ext, dim3(kh, n_xi), dim3(chi <= 8 ? 64 : 256), energy_smem(chi), h->stream, (const cplx*)dM, (const long*)dOff,
-             (const int*)dBond, n_sites, n_phys, chi, (const uint8_t*)dHb, (const cplx*)dPh, kh, dT);
+  if (chi > 16)
+    DQA_LAUNCH(k_energy_ext<true>, dim3(kh, n_xi), dim3(256), energy_smem(chi), h->stream, (const cplx*)dM, (const long*)dOff,
+               (const int*)dBond, n_sites, n_phys, chi, (const uint8_t*)dHb, (const cplx*)dPh, kh, dT);
+  else
+    DQA_LAUNCH(k_energy_ext<false>, dim3(kh, n_xi), dim3(chi <= 8 ? 64 : 256), energy_smem(chi), h->stream, (const cplx*)dM,
+               (const long*)dOff, (const int*)dBond, n_sites, n_phys, chi, (const uint8_t*)dHb, (const cplx*)dPh, kh, dT);
   DQA_LAUNCH(k_energy_ext_reduce, dim3(1), dim3(32), 0, h->stream, (const cplx*)dT, (const cplx*)dGk, n_xi, kh, D, n_phys, dE);
   OCK(cudaGetLastError());
   OCK(cudaMemcpyAsync(eps, dE, sizeof(cplx), cudaMemcpyDeviceToHost, h->stream));

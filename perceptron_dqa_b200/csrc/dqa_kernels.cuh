@@ -557,36 +557,48 @@ __global__ void __launch_bounds__(1024) k_lq(DqaDev d, int l) {
       Vp[r * npad + c] = src[(size_t)(p0 + r) * ld + p0 + c];
     }
     __syncthreads();
+    tl_t += clock64() - tl0;  // panel load (reported as the "tmat" counter)
     // ---- factor the panel (rows p0..p0+pb-1), unblocked, in shared memory ----
     // (a column-distributed variant with one fused reduction per reflector was tried and measured slower
     //  under load: 203 vs 187 ms per step at batch 888)
-    for (int i = 0; i < pb; ++i) {
+    // One block barrier per reflector: while the other warps apply reflector i to their rows, warp 0 (which always
+    // owns row i+1) accumulates the norm of its updated row inside the update loop, then generates and scales
+    // reflector i+1 straight away.
+    auto gen_row = [&](int i, double ss) {  // warp 0; ss = sum_{c>i} |row_i[c]|^2, already reduced
       cplx* row = Vp + i * npad;
-      if (warp == 0) {
-        double ss0 = 0.0, ss1 = 0.0;
-        for (int c = i + 1 + lane; c < n; c += 64) {
-          ss0 += cabs2(row[c]);
-          if (c + 32 < n) ss1 += cabs2(row[c + 32]);
-        }
-        const double ss = warp_sum(ss0 + ss1);
-        const cplx alpha = row[i];
-        double beta;
-        cplx t, scal;
-        householder_gen_fast(cconj(alpha), ss, beta, t, scal);
-        const cplx cs = cconj(scal);  // stored vector is conj(v)
-        __syncwarp();
-        for (int c = i + 1 + lane; c < n; c += 32) row[c] = cmul(row[c], cs);
-        if (lane == 0) {
-          taus[i] = t;
-          row[i] = cmk(beta, 0.0);
-        }
+      const cplx alpha = row[i];
+      double beta;
+      cplx t, scal;
+      householder_gen_fast(cconj(alpha), ss, beta, t, scal);
+      const cplx cs = cconj(scal);  // stored vector is conj(v)
+      __syncwarp();
+#pragma unroll 4
+      for (int c = i + 1 + lane; c < n; c += 32) row[c] = cmul(row[c], cs);
+      if (lane == 0) {
+        taus[i] = t;
+        row[i] = cmk(beta, 0.0);
       }
-      __syncthreads();
+    };
+    if (warp == 0) {
+      double ss0 = 0.0, ss1 = 0.0;
+      for (int c = 1 + lane; c < n; c += 64) {
+        ss0 += cabs2(Vp[c]);
+        if (c + 32 < n) ss1 += cabs2(Vp[c + 32]);
+      }
+      gen_row(0, warp_sum(ss0 + ss1));
+    }
+    __syncthreads();
+    for (int i = 0; i < pb; ++i) {
+      const cplx* __restrict__ row = Vp + i * npad;
       const cplx t = taus[i];
-      if (t.x != 0.0 || t.y != 0.0) {
-        for (int r = i + 1 + warp; r < pb; r += nwarp) {
-          cplx* yr = Vp + r * npad;
+      const bool rot = (t.x != 0.0 || t.y != 0.0);
+      double ssn = 0.0;
+      for (int r = i + 1 + warp; r < pb; r += nwarp) {
+        cplx* __restrict__ yr = Vp + r * npad;  // a different row than `row`: loads may be hoisted above the stores
+        const bool next = (r == i + 1);  // warp 0's first row: the next reflector
+        if (rot) {
           cplx w0 = (lane == 0) ? yr[i] : cmk(0.0, 0.0), w1 = cmk(0.0, 0.0);
+#pragma unroll 2
           for (int c = i + 1 + lane; c < n; c += 64) {
             w0 = cfmac(yr[c], row[c], w0);
             if (c + 32 < n) w1 = cfmac(yr[c + 32], row[c + 32], w1);
@@ -594,8 +606,24 @@ __global__ void __launch_bounds__(1024) k_lq(DqaDev d, int l) {
           const cplx w = warp_sum(cadd(w0, w1));
           const cplx tw = cmul(t, w);
           if (lane == 0) yr[i] = csub(yr[i], tw);
-          for (int c = i + 1 + lane; c < n; c += 32) yr[c] = cfms(tw, row[c], yr[c]);
+          if (next) {
+#pragma unroll 4
+            for (int c = i + 1 + lane; c < n; c += 32) {
+              const cplx yv = cfms(tw, row[c], yr[c]);
+              yr[c] = yv;
+              if (c > i + 1) ssn += cabs2(yv);
+            }
+          } else {
+#pragma unroll 4
+            for (int c = i + 1 + lane; c < n; c += 32) yr[c] = cfms(tw, row[c], yr[c]);
+          }
+        } else if (next) {
+          for (int c = i + 2 + lane; c < n; c += 32) ssn += cabs2(yr[c]);
         }
+      }
+      if (warp == 0 && i + 1 < pb) {
+        __syncwarp();
+        gen_row(i + 1, warp_sum(ssn));
       }
       __syncthreads();
     }
@@ -618,7 +646,6 @@ __global__ void __launch_bounds__(1024) k_lq(DqaDev d, int l) {
     tl_panel += tl1 - tl0;
     if (r_first < mr) {
       const long long tl2 = clock64();
-      tl_t += tl2 - tl1;
       // ---- trailing rows with FP64 tensor-core tiles --------------------------------------------------
       // pass 1: W = Y V for every 8-row tile of trailing rows, plus one extra tile with Y = the panel
       //         itself, which yields S = V^H V (the Gram matrix of the reflectors); K split over warps.

@@ -37,6 +37,7 @@ NCU_KEEP = [
     "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
     "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio",
     "smsp__inst_executed.sum", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+    "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed", "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct",
 ]
 
 
@@ -103,6 +104,8 @@ def main():
     ncu_summary(f"prof_jac_{t}.ncu-rep", "k_jacobi", t)
     ncu_summary(f"prof_sqr_{t}.ncu-rep", "k_sector_qr", t)
     ncu_summary(f"prof_lq_{t}.ncu-rep", "k_lq", t)
+    ncu_summary(f"prof_energy_{t}.ncu-rep", "k_energy", t)
+    ncu_summary(f"prof_theta_{t}.ncu-rep", "k_theta", t)
 
 
 if __name__ == "__main__":

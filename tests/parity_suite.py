@@ -186,3 +186,25 @@ def check_small_edge_cases(factory, cases=None):
         assert list(pl.bd_monitor()[0]) == ref.bd_monitor, (n, n_xi, chi, P)
         assert abs(O.fidelity_defect(pl.get_mps(0), ref.psi)) < 1e-11
         assert not pl.status().any()
+
+
+def check_bond_sweep(factory, chis=(12, 20, 24, 28), n=12, n_xi=5, P=6, steps=3, dt=0.8):
+    """Bond dimensions that are not powers of two (column-pair counts that do not fill the Jacobi kernel's warps, odd
+    numbers of LQ panels, ragged DMMA tiles): first steps of a run on iid patterns against the oracle run on the fly."""
+    rng = np.random.default_rng(29)
+    xi = (2 * rng.integers(0, 2, size=(n_xi, n)) - 1).astype(np.int8)
+    for chi in chis:
+        ref = O.OracleDQA(xi, P, dt, chi, fast_loss=True)
+        ref.init_fourier()
+        ref.run(steps=steps)
+        pl = factory(n, n_xi, P, dt, chi, 1)
+        pl.set_patterns(xi[None])
+        pl.set_fourier(ref.Uk_FT, ref.fxft)
+        pl.reset_plus()
+        pl.step(steps)
+        got = pl.eps_trace()[0, : steps + 1]
+        want = np.array([l[1] for l in ref.loss])
+        assert np.abs(got - want).max() < 1e-10, (chi, np.abs(got - want).max())
+        assert list(pl.bd_monitor()[0, : steps * n_xi]) == ref.bd_monitor, chi
+        assert abs(O.fidelity_defect(pl.get_mps(0), ref.psi)) < 1e-10, chi
+        assert not pl.status().any()

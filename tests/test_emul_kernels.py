@@ -51,6 +51,10 @@ def test_small_edge_cases(factory):
     ps.check_small_edge_cases(factory)
 
 
+def test_bond_sweep_non_power_of_two(factory):
+    ps.check_bond_sweep(factory, chis=(6, 12), n=8, n_xi=3, P=4, steps=2)
+
+
 def test_teacher_forced_n12_one_substep(factory):
     ps.check_teacher_forced(factory, "c1_n12_chi10", max_snaps=1)
 

@@ -258,6 +258,10 @@ def test_small_edge_cases(factory):
     ps.check_small_edge_cases(factory)
 
 
+def test_bond_sweep_non_power_of_two(factory):
+    ps.check_bond_sweep(factory)
+
+
 def test_driver_class_matches_fixture():
     """The mydQA drop-in: construct -> init_fourier -> run -> loss[-1][1] (benchmarker-mps.py:32-43)."""
     from perceptron_dqa_b200.dQA_mps import mydQA

@@ -55,6 +55,11 @@ def test_bond_sweep_non_power_of_two(factory):
     ps.check_bond_sweep(factory, chis=(6, 12), n=8, n_xi=3, P=4, steps=2)
 
 
+def test_bond_above_16_uses_the_eight_row_kernels(factory):
+    # chi in (16,32]: k_sector_qr<8>, k_jacobi_sys<8> and the paired DMMA tiles (bond 20 is reached at N=10)
+    ps.check_bond_sweep(factory, chis=(20,), n=10, n_xi=2, P=3, steps=1)
+
+
 def test_teacher_forced_n12_one_substep(factory):
     ps.check_teacher_forced(factory, "c1_n12_chi10", max_snaps=1)
 

@@ -1416,7 +1416,7 @@ __device__ __forceinline__ cplx energy_sweep(const EnergyView& v, const uint8_t*
 }
 
 template <bool PAIR>
-__global__ void __launch_bounds__(256, 3) k_energy(DqaDev d) {
+__global__ void __launch_bounds__(256, PAIR ? 3 : 4) k_energy(DqaDev d) {
   DQA_DYN_SMEM(smraw);
   const int k = blockIdx.x, mu = blockIdx.y, inst = blockIdx.z;
   EnergyView v;

@@ -21,10 +21,8 @@
 #endif
 
 // template instances with a comma in their argument list, named so they can pass through macros
-static void (*const KJ_0S)(DqaDev, int, int, int) = k_jacobi<0, true>;
-static void (*const KJ_0G)(DqaDev, int, int, int) = k_jacobi<0, false>;
-static void (*const KJ_4S)(DqaDev, int, int, int) = k_jacobi<4, true>;
-static void (*const KJ_8S)(DqaDev, int, int, int) = k_jacobi<8, true>;
+static void (*const KJ_0S)(DqaDev, int, int, int) = k_jacobi<true>;
+static void (*const KJ_0G)(DqaDev, int, int, int) = k_jacobi<false>;
 static void (*const KE_1)(DqaDev) = k_energy<false>;
 static void (*const KE_2)(DqaDev) = k_energy<true>;
 static void (*const KJ_Y2)(DqaDev, int, int, int) = k_jacobi_sys<2>;
@@ -44,7 +42,7 @@ struct dqa_handle {
   bool have_patterns, have_fourier, have_state;
   int t_qr, t_theta, t_svd, t_energy;  // block sizes
   int t_lq;
-  bool jac_nocache, jac_cache32, jac_sys;
+  bool jac_sys;
   char err[512];
   // profiling
   bool profiling;
@@ -183,7 +181,6 @@ extern "C" int dqa_create(dqa_t** out, const dqa_config* cfg) {
 #ifdef DQA_EMUL
   h->t_qr = 32 * ((8 * c.chi + 31) / 32); h->t_theta = 64; h->t_svd = 64; h->t_energy = 64; h->t_lq = 64;
   if (h->t_qr < 64) h->t_qr = 64;
-  h->jac_nocache = false; h->jac_cache32 = true;
 #else
   h->t_qr = 32 * ((8 * c.chi + 31) / 32);  // one 8-lane group per column of the sector block
   if (h->t_qr < 64) h->t_qr = 64;
@@ -197,9 +194,6 @@ extern "C" int dqa_create(dqa_t** out, const dqa_config* cfg) {
     if (env && atoi(env) >= 1 && atoi(env) <= 16) warps = atoi(env);
     if (warps < (c.chi + 31) / 32) warps = (c.chi + 31) / 32;  // at most 32 column pairs per warp
     h->t_svd = 32 * warps;
-    env = getenv("DQA_JAC_CACHE");  // 0: never keep the pair in registers; 2: also for chi in (16,32] (costs occupancy)
-    h->jac_nocache = env && atoi(env) == 0;
-    h->jac_cache32 = env && atoi(env) == 2;
     h->t_lq = c.chi <= 8 ? 128 : (c.chi <= 16 ? 256 : 512);
     env = getenv("DQA_LQ_THREADS");
     if (env && atoi(env) >= 32 && atoi(env) <= 32 * LQ_MAXW) h->t_lq = atoi(env) & ~31;
@@ -218,8 +212,6 @@ extern "C" int dqa_create(dqa_t** out, const dqa_config* cfg) {
   CK(cudaFuncSetAttribute(k_sector_qr<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sector_qr_smem(c.chi)));
   CK(cudaFuncSetAttribute(KJ_0S, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)svd_smem(c.chi)));
   CK(cudaFuncSetAttribute(KJ_0G, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)svd_smem(c.chi)));
-  CK(cudaFuncSetAttribute(KJ_4S, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)svd_smem(c.chi)));
-  CK(cudaFuncSetAttribute(KJ_8S, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)svd_smem(c.chi)));
   if (c.chi <= 32) {
     CK(cudaFuncSetAttribute(KJ_Y2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)svd_smem(c.chi)));
     CK(cudaFuncSetAttribute(KJ_Y4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)svd_smem(c.chi)));
@@ -417,14 +409,11 @@ static int launch_truncate(dqa_t* h, int p, int mu) {
     prof_b(h);
     prof_a(h, 5);
     {
-      // register-cached variant needs one pass per round (4 pairs per warp) and 2chi <= 8*RS rows
-      const bool one_pass = (h->t_svd / 32) * 4 >= d.chi;
+      // chi <= 32: the systolic kernel (2chi <= 8 RS rows per column); above: L in shared memory (chi <= 56) or in L2
       const int t_sys = 32 * ((d.chi + 3) / 4);  // one 8-lane group per column pair
       if (h->jac_sys && d.chi <= 8) HL(KJ_Y2, dim3(d.batch), dim3(t_sys), svd_smem(d.chi), h->stream, d, l, mu, p);
       else if (h->jac_sys && d.chi <= 16) HL(KJ_Y4, dim3(d.batch), dim3(t_sys), svd_smem(d.chi), h->stream, d, l, mu, p);
       else if (h->jac_sys && d.chi <= 32) HL(KJ_Y8, dim3(d.batch), dim3(t_sys), svd_smem(d.chi), h->stream, d, l, mu, p);
-      else if (one_pass && d.chi <= 16 && !h->jac_nocache) HL(KJ_4S, dim3(d.batch), dim3(h->t_svd), svd_smem(d.chi), h->stream, d, l, mu, p);
-      else if (one_pass && d.chi <= 32 && h->jac_cache32) HL(KJ_8S, dim3(d.batch), dim3(h->t_svd), svd_smem(d.chi), h->stream, d, l, mu, p);
       else if (svd_l_in_smem(d.chi)) HL(KJ_0S, dim3(d.batch), dim3(h->t_svd), svd_smem(d.chi), h->stream, d, l, mu, p);
       else HL(KJ_0G, dim3(d.batch), dim3(h->t_svd), svd_smem(d.chi), h->stream, d, l, mu, p);
     }

@@ -752,7 +752,7 @@ __global__ void __launch_bounds__(1024) k_lq(DqaDev d, int l) {
 }
 
 // ---------------------------------------------------------------------------------
-// k_jacobi: SVD of L (mr x k) by one-sided Jacobi + the reference's trim rule
+// k_jacobi (bonds above 32; k_jacobi_sys below handles chi <= 32): SVD of L (mr x k) by one-sided Jacobi + the reference's trim rule
 // (lib/tenn.py:317-354) + the new left-orthonormal site tensor (lib/tenn.py:229-252).
 // Few warps per CTA (several CTAs share an SM): every warp owns ppw column pairs per round;
 // the complex dot products are reduced with warp shuffles; the rotation parameters of the
@@ -863,9 +863,7 @@ __device__ __forceinline__ void jacobi_tail(const DqaDev& d, int inst, int l, in
   }
 }
 
-#define JAC_UN 4
-template <int RS, bool LSM>  // RS > 0: one pass per round, the pair's rows (li+8t, t<RS) stay in registers between dot and
-                             // rotation; LSM: L lives in shared memory (compile-time, so its accesses are LDS/STS)
+template <bool LSM>  // LSM: L lives in shared memory (compile-time, so its accesses are LDS/STS)
 __global__ void __launch_bounds__(512) k_jacobi(DqaDev d, int l, int mu, int p_step) {
   DQA_DYN_SMEM(smraw);
   const int inst = blockIdx.x, tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarp = nt >> 5;
@@ -927,7 +925,6 @@ __global__ void __launch_bounds__(512) k_jacobi(DqaDev d, int l, int mu, int p_s
       bool myact = false;
       double mya = 0.0, myb = 0.0;
       const bool onepass = npass == 1;  // then every lane of a group keeps the pair's data: no broadcasts needed
-      cplx vp[RS > 0 ? RS : 1], vq[RS > 0 ? RS : 1];
       for (int pass = 0; pass < npass; ++pass) {
         const int u = pass * 4 + grp, pr = warp * ppw + u;
         int p = 0, q = 0;
@@ -942,18 +939,7 @@ __global__ void __launch_bounds__(512) k_jacobi(DqaDev d, int l, int mu, int p_s
           a0 = nrm2[p];
           b0 = nrm2[q];
         }
-        if (RS > 0) {
-          const cplx* xp = L + p * ldl;
-          const cplx* xq = L + q * ldl;
-#pragma unroll
-          for (int t = 0; t < (RS > 0 ? RS : 1); ++t) {
-            const int r = li + 8 * t;
-            const bool in = act && r < mr;
-            vp[t] = in ? xp[r] : cmk(0.0, 0.0);
-            vq[t] = in ? xq[r] : cmk(0.0, 0.0);
-            g = cfmac(vq[t], vp[t], g);
-          }
-        } else if (act) {
+        if (act) {
           const cplx* xp = L + p * ldl;
           const cplx* xq = L + q * ldl;
           for (int r = li; r < mr; r += 8) g = cfmac(xq[r], xp[r], g);  // conj(xp) * xq
@@ -970,7 +956,7 @@ __global__ void __launch_bounds__(512) k_jacobi(DqaDev d, int l, int mu, int p_s
           mya = a0;
           myb = b0;
         }
-        if (li == pass || RS > 0 || onepass) {
+        if (li == pass || onepass) {
           myp = p;
           myq = q;
         }
@@ -1019,10 +1005,8 @@ __global__ void __launch_bounds__(512) k_jacobi(DqaDev d, int l, int mu, int p_s
           const int src = (lane & ~7) | pass;
           dr = __shfl_sync(DQA_FULL, rot, src);
           if (!__any_sync(DQA_FULL, dr)) continue;  // warp-uniform
-          if (RS == 0) {
-            p = __shfl_sync(DQA_FULL, myp, src);
-            q = __shfl_sync(DQA_FULL, myq, src);
-          }
+          p = __shfl_sync(DQA_FULL, myp, src);
+          q = __shfl_sync(DQA_FULL, myq, src);
           c = __shfl_sync(DQA_FULL, rc, src);
           sn = __shfl_sync(DQA_FULL, rsn, src);
           sph = cmk(__shfl_sync(DQA_FULL, rsph.x, src), __shfl_sync(DQA_FULL, rsph.y, src));
@@ -1031,21 +1015,10 @@ __global__ void __launch_bounds__(512) k_jacobi(DqaDev d, int l, int mu, int p_s
         if (dr) {
           cplx* xp = L + p * ldl;
           cplx* xq = L + q * ldl;
-          if (RS > 0) {
-#pragma unroll
-            for (int t = 0; t < (RS > 0 ? RS : 1); ++t) {
-              const int r = li + 8 * t;
-              if (r < mr) {
-                xp[r] = cfms(sph, vq[t], cscale(vp[t], c));   // c*xp - s e^{-i phi} xq
-                xq[r] = cfma(cph, vq[t], cscale(vp[t], sn));  // s*xp + c e^{-i phi} xq
-              }
-            }
-          } else {
-            for (int r = li; r < mr; r += 8) {
-              const cplx a_ = xp[r], b_ = xq[r];
-              xp[r] = cfms(sph, b_, cscale(a_, c));
-              xq[r] = cfma(cph, b_, cscale(a_, sn));
-            }
+          for (int r = li; r < mr; r += 8) {
+            const cplx a_ = xp[r], b_ = xq[r];
+            xp[r] = cfms(sph, b_, cscale(a_, c));   // c*xp - s e^{-i phi} xq
+            xq[r] = cfma(cph, b_, cscale(a_, sn));  // s*xp + c e^{-i phi} xq
           }
         }
       }

@@ -262,6 +262,11 @@ def test_bond_sweep_non_power_of_two(factory):
     ps.check_bond_sweep(factory)
 
 
+def test_bond_sweep_above_32(factory):
+    # chi in (32,56]: k_sector_qr<12>/<16> and the shared-memory-resident Jacobi kernel
+    ps.check_bond_sweep(factory, chis=(40, 48, 56), steps=2)
+
+
 def test_driver_class_matches_fixture():
     """The mydQA drop-in: construct -> init_fourier -> run -> loss[-1][1] (benchmarker-mps.py:32-43)."""
     from perceptron_dqa_b200.dQA_mps import mydQA

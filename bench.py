@@ -336,6 +336,21 @@ def run_ours(a):
             "reference_algorithm": {"flops_per_realisation_step": reference_flops(a.n, a.nxi, a.chi),
                                     "executed_flops_per_realisation_step": float(sum(flops.values())) / B},
         }
+        # DRAM traffic of the dominant kernel: not measurable here without a profiler, so it is read from the committed ncu
+        # capture of the same kernel (one mid-chain launch at this batch), when that summary is present
+        try:
+            tr = 0.0
+            with open(os.path.join(ROOT, "profiles", f"r01_{line['roofline']['kernel']}_ncu_summary.csv")) as f:
+                for ln in f:
+                    parts = ln.strip().split(",")
+                    if len(parts) == 3 and parts[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                        tr += float(parts[2]) * {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[parts[1]]
+            if tr > 0:
+                line["roofline"]["traffic"] = tr
+                line["roofline"]["traffic_source"] = (f"profiles/r01_{line['roofline']['kernel']}_ncu_summary.csv: dram read+write of one "
+                                                      "launch under ncu --set full (batch 888); the kernel is FP64-bound, not HBM-bound")
+        except Exception:
+            pass
         # the HBM side of the roofline, to show the step is not bandwidth bound: algorithmic bytes = the MPS read and
         # written once per pattern sub-step and once for mixer+energy, against the pool's measured copy bandwidth
         try:

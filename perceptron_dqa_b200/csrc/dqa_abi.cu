@@ -208,6 +208,7 @@ extern "C" int dqa_create(dqa_t** out, const dqa_config* cfg) {
   CK(cudaFuncSetAttribute(k_sector_qr<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sector_qr_smem(c.chi)));
   CK(cudaFuncSetAttribute(k_sector_qr<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sector_qr_smem(c.chi)));
   CK(cudaFuncSetAttribute(k_sector_qr<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sector_qr_smem(c.chi)));
+  CK(cudaFuncSetAttribute(k_sector_qr<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sector_qr_smem(c.chi)));
   CK(cudaFuncSetAttribute(k_sector_qr<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sector_qr_smem(c.chi)));
   CK(cudaFuncSetAttribute(k_sector_qr<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sector_qr_smem(c.chi)));
   CK(cudaFuncSetAttribute(KJ_0S, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)svd_smem(c.chi)));
@@ -385,6 +386,7 @@ static int launch_canonize(dqa_t* h, int mu) {
     if (d.chi <= 8) HL(k_sector_qr<2>, grid, block, sm, h->stream, d, n, mu);
     else if (d.chi <= 16) HL(k_sector_qr<4>, grid, block, sm, h->stream, d, n, mu);
     else if (d.chi <= 32) HL(k_sector_qr<8>, grid, block, sm, h->stream, d, n, mu);
+    else if (d.chi <= 40) HL(k_sector_qr<10>, grid, block, sm, h->stream, d, n, mu);
     else if (d.chi <= 48) HL(k_sector_qr<12>, grid, block, sm, h->stream, d, n, mu);
     else HL(k_sector_qr<16>, grid, block, sm, h->stream, d, n, mu);
     prof_b(h);

@@ -26,7 +26,9 @@ static void (*const KJ_0G)(DqaDev, int, int, int) = k_jacobi<false>;
 static void (*const KE_1)(DqaDev) = k_energy<false>;
 static void (*const KE_2)(DqaDev) = k_energy<true>;
 static void (*const KJ_Y2)(DqaDev, int, int, int) = k_jacobi_sys<2>;
+static void (*const KJ_Y3)(DqaDev, int, int, int) = k_jacobi_sys<3>;
 static void (*const KJ_Y4)(DqaDev, int, int, int) = k_jacobi_sys<4>;
+static void (*const KJ_Y6)(DqaDev, int, int, int) = k_jacobi_sys<6>;
 static void (*const KJ_Y8)(DqaDev, int, int, int) = k_jacobi_sys<8>;
 
 struct dqa_handle {
@@ -206,7 +208,9 @@ extern "C" int dqa_create(dqa_t** out, const dqa_config* cfg) {
   }
   CK(cudaSetDevice(c.device));
   CK(cudaFuncSetAttribute(k_sector_qr<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sector_qr_smem(c.chi)));
+  CK(cudaFuncSetAttribute(k_sector_qr<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sector_qr_smem(c.chi)));
   CK(cudaFuncSetAttribute(k_sector_qr<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sector_qr_smem(c.chi)));
+  CK(cudaFuncSetAttribute(k_sector_qr<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sector_qr_smem(c.chi)));
   CK(cudaFuncSetAttribute(k_sector_qr<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sector_qr_smem(c.chi)));
   CK(cudaFuncSetAttribute(k_sector_qr<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sector_qr_smem(c.chi)));
   CK(cudaFuncSetAttribute(k_sector_qr<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sector_qr_smem(c.chi)));
@@ -215,7 +219,9 @@ extern "C" int dqa_create(dqa_t** out, const dqa_config* cfg) {
   CK(cudaFuncSetAttribute(KJ_0G, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)svd_smem(c.chi)));
   if (c.chi <= 32) {
     CK(cudaFuncSetAttribute(KJ_Y2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)svd_smem(c.chi)));
+    CK(cudaFuncSetAttribute(KJ_Y3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)svd_smem(c.chi)));
     CK(cudaFuncSetAttribute(KJ_Y4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)svd_smem(c.chi)));
+    CK(cudaFuncSetAttribute(KJ_Y6, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)svd_smem(c.chi)));
     CK(cudaFuncSetAttribute(KJ_Y8, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)svd_smem(c.chi)));
   }
   CK(cudaFuncSetAttribute(k_lq, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lq_smem(h->dev.qmax, c.chi, h->dev.lq_pb)));
@@ -384,7 +390,9 @@ static int launch_canonize(dqa_t* h, int mu) {
     const dim3 grid(d.N - n + 1, d.batch), block(h->t_qr);
     const size_t sm = sector_qr_smem(d.chi);
     if (d.chi <= 8) HL(k_sector_qr<2>, grid, block, sm, h->stream, d, n, mu);
+    else if (d.chi <= 12) HL(k_sector_qr<3>, grid, block, sm, h->stream, d, n, mu);
     else if (d.chi <= 16) HL(k_sector_qr<4>, grid, block, sm, h->stream, d, n, mu);
+    else if (d.chi <= 24) HL(k_sector_qr<6>, grid, block, sm, h->stream, d, n, mu);
     else if (d.chi <= 32) HL(k_sector_qr<8>, grid, block, sm, h->stream, d, n, mu);
     else if (d.chi <= 40) HL(k_sector_qr<10>, grid, block, sm, h->stream, d, n, mu);
     else if (d.chi <= 48) HL(k_sector_qr<12>, grid, block, sm, h->stream, d, n, mu);
@@ -414,7 +422,9 @@ static int launch_truncate(dqa_t* h, int p, int mu) {
       // chi <= 32: the systolic kernel (2chi <= 8 RS rows per column); above: L in shared memory (chi <= 56) or in L2
       const int t_sys = 32 * ((d.chi + 3) / 4);  // one 8-lane group per column pair
       if (h->jac_sys && d.chi <= 8) HL(KJ_Y2, dim3(d.batch), dim3(t_sys), svd_smem(d.chi), h->stream, d, l, mu, p);
+      else if (h->jac_sys && d.chi <= 12) HL(KJ_Y3, dim3(d.batch), dim3(t_sys), svd_smem(d.chi), h->stream, d, l, mu, p);
       else if (h->jac_sys && d.chi <= 16) HL(KJ_Y4, dim3(d.batch), dim3(t_sys), svd_smem(d.chi), h->stream, d, l, mu, p);
+      else if (h->jac_sys && d.chi <= 24) HL(KJ_Y6, dim3(d.batch), dim3(t_sys), svd_smem(d.chi), h->stream, d, l, mu, p);
       else if (h->jac_sys && d.chi <= 32) HL(KJ_Y8, dim3(d.batch), dim3(t_sys), svd_smem(d.chi), h->stream, d, l, mu, p);
       else if (svd_l_in_smem(d.chi)) HL(KJ_0S, dim3(d.batch), dim3(h->t_svd), svd_smem(d.chi), h->stream, d, l, mu, p);
       else HL(KJ_0G, dim3(d.batch), dim3(h->t_svd), svd_smem(d.chi), h->stream, d, l, mu, p);

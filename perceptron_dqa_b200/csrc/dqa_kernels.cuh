@@ -121,7 +121,7 @@ __global__ void k_init_plus(DqaDev d) {
 #ifndef SQR_MINB
 #define SQR_MINB 3  // CTAs per SM the 8-slot sector-QR kernel is compiled for
 #endif
-__host__ __device__ inline int sector_qr_maxs(int chi) { return chi <= 8 ? 2 : (chi <= 16 ? 4 : (chi <= 32 ? 8 : (chi <= 40 ? 10 : (chi <= 48 ? 12 : 16)))); }
+__host__ __device__ inline int sector_qr_maxs(int chi) { return chi <= 8 ? 2 : (chi <= 12 ? 3 : (chi <= 16 ? 4 : (chi <= 24 ? 6 : (chi <= 32 ? 8 : (chi <= 40 ? 10 : (chi <= 48 ? 12 : 16)))))); }
 __host__ __device__ inline size_t sector_qr_smem(int chi) {  // M has 8*MAXS rows so every register slot has a row
   return sizeof(cplx) * ((size_t)8 * sector_qr_maxs(chi) * chi + chi) + sizeof(double) * chi;
 }
@@ -225,7 +225,7 @@ __device__ __forceinline__ void sqr_apply(cplx (&col)[MAXS], const cplx* vk, cpl
 }
 
 template <int MAXS>
-__global__ void __launch_bounds__(MAXS <= 8 ? 256 : (MAXS == 10 ? 320 : (MAXS == 12 ? 384 : 512)), MAXS <= 4 ? 4 : (MAXS == 8 ? SQR_MINB : (MAXS == 10 ? 2 : 1))) k_sector_qr(DqaDev d, int n, int mu) {
+__global__ void __launch_bounds__(MAXS <= 8 ? 256 : (MAXS == 10 ? 320 : (MAXS == 12 ? 384 : 512)), MAXS <= 4 ? 4 : (MAXS <= 8 ? SQR_MINB : (MAXS == 10 ? 2 : 1))) k_sector_qr(DqaDev d, int n, int mu) {
   DQA_DYN_SMEM(smraw);
   const int y = blockIdx.x, inst = blockIdx.y;
   const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarp = nt >> 5;
@@ -1056,7 +1056,7 @@ __global__ void __launch_bounds__(512) k_jacobi(DqaDev d, int l, int mu, int p_s
 // shared: exchange buffers 2 x (groups x mr), reused for the final columns | sig | xn/ssorted | order | sh_i
 // ---------------------------------------------------------------------------------
 template <int RS>
-__global__ void __launch_bounds__(RS * 32, RS >= 8 ? 2 : (RS >= 4 ? 6 : 8)) k_jacobi_sys(DqaDev d, int l, int mu, int p_step) {
+__global__ void __launch_bounds__(RS * 32, RS >= 8 ? 2 : (RS >= 6 ? 3 : (RS >= 4 ? 6 : 8))) k_jacobi_sys(DqaDev d, int l, int mu, int p_step) {
   DQA_DYN_SMEM(smraw);
   const int inst = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
   const int chi = d.chi;

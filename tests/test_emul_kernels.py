@@ -55,9 +55,10 @@ def test_bond_sweep_non_power_of_two(factory):
     ps.check_bond_sweep(factory, chis=(6, 12), n=8, n_xi=3, P=4, steps=2)
 
 
-def test_bond_above_16_uses_the_eight_row_kernels(factory):
-    # chi in (16,32]: k_sector_qr<8>, k_jacobi_sys<8> and the paired DMMA tiles (bond 20 is reached at N=10)
-    ps.check_bond_sweep(factory, chis=(20,), n=10, n_xi=2, P=3, steps=1)
+def test_bond_above_16_uses_the_six_and_eight_slot_kernels(factory):
+    # chi in (16,24]: k_sector_qr<6>, k_jacobi_sys<6>; chi in (24,32]: the <8> ones; both with the paired DMMA tiles
+    # (bonds 20 and 28 are reached at N=10)
+    ps.check_bond_sweep(factory, chis=(20, 28), n=10, n_xi=2, P=3, steps=1)
 
 
 def test_teacher_forced_n12_one_substep(factory):

@@ -42,7 +42,7 @@ struct dqa_handle {
   int32_t* d_q;
   int pp;
   bool have_patterns, have_fourier, have_state;
-  int t_qr, t_theta, t_svd, t_energy;  // block sizes
+  int t_qr, t_theta, t_svd, t_energy, t_energy_env = 0;  // block sizes
   int t_lq;
   bool jac_sys;
   char err[512];
@@ -186,7 +186,15 @@ extern "C" int dqa_create(dqa_t** out, const dqa_config* cfg) {
 #else
   h->t_qr = 32 * ((8 * c.chi + 31) / 32);  // one 8-lane group per column of the sector block
   if (h->t_qr < 64) h->t_qr = 64;
-  h->t_theta = 256;
+  // measured (tools/block_size_sweep.py, batch 888): the tile counts of the two contraction kernels grow as (chi/8)^2, and
+  // CTAs no larger than their task count win by a wide margin at small bonds (chi=10: theta 34 -> 14 ms per step)
+  h->t_theta = c.chi <= 12 ? 32 : (c.chi <= 24 ? 64 : (c.chi <= 32 ? 128 : 256));
+  {
+    const char* env = getenv("DQA_THETA_THREADS");
+    if (env && atoi(env) >= 32 && atoi(env) <= 256) h->t_theta = atoi(env) & ~31;
+    env = getenv("DQA_ENERGY_THREADS");
+    if (env && atoi(env) >= 32 && atoi(env) <= 256) h->t_energy_env = atoi(env) & ~31;
+  }
   {
     // Jacobi: few warps per CTA, each owning ~8 column pairs per round; several CTAs share an SM
     int warps = (c.chi + 3) / 4;  // 4 column pairs per warp and round: one pass per round
@@ -196,11 +204,12 @@ extern "C" int dqa_create(dqa_t** out, const dqa_config* cfg) {
     if (env && atoi(env) >= 1 && atoi(env) <= 16) warps = atoi(env);
     if (warps < (c.chi + 31) / 32) warps = (c.chi + 31) / 32;  // at most 32 column pairs per warp
     h->t_svd = 32 * warps;
-    h->t_lq = c.chi <= 8 ? 128 : (c.chi <= 16 ? 256 : 512);
+    h->t_lq = c.chi <= 8 ? 128 : (c.chi <= 24 ? 256 : 512);
     env = getenv("DQA_LQ_THREADS");
     if (env && atoi(env) >= 32 && atoi(env) <= 32 * LQ_MAXW) h->t_lq = atoi(env) & ~31;
   }
-  h->t_energy = c.chi <= 8 ? 64 : 256;
+  h->t_energy = c.chi <= 16 ? 64 : (c.chi <= 24 ? 128 : 256);
+  if (h->t_energy_env) h->t_energy = h->t_energy_env;
 #endif
   {
     const char* env = getenv("DQA_JAC_SYS");  // 0: use the shared-memory-resident Jacobi for every chi

@@ -15,7 +15,7 @@ for arg in sys.argv[2:]:
         env["DQA_LQ_THREADS"] = t
     else:
         env["DQA_THETA_THREADS"] = env["DQA_ENERGY_THREADS"] = t
-    out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "profile_step.py"), "--chi", chi, "--batch", "888", "--steps", "2",
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "profile_step.py"), "--chi", chi, "--batch", os.environ.get("SWEEP_BATCH", "888"), "--steps", "2",
                           "--warmup", "1"], env=env, capture_output=True, text=True).stdout.strip().split("\n")[-1]
     d = json.loads(out)
     keys = ("lq",) if what == "lq" else ("theta", "energy")

@@ -710,9 +710,35 @@ __global__ void __launch_bounds__(1024) k_lq(DqaDev d, int l) {
       }
       __syncthreads();
       const int ntc = (n + 7) >> 3;
+      // the Y entries of the NEXT tile are requested before the current tile's small GEMM, so their L2/HBM latency
+      // overlaps it (one tile of look-ahead is what the 64-register budget allows)
+      cplx yn0 = cmk(0.0, 0.0), yn1 = cmk(0.0, 0.0);
+      {
+        const int tile = warp;
+        if (tile < ntr * ntc) {
+          const int r = r_first + (tile / ntc) * 8 + g, c = (tile % ntc) * 8 + 2 * t4;
+          if (r < mr) {
+            const cplx* ys = src + (size_t)r * ld + p0;
+            if (c < n) yn0 = ys[c];
+            if (c + 1 < n) yn1 = ys[c + 1];
+          }
+        }
+      }
       for (int tile = warp; tile < ntr * ntc; tile += nwarp) {
         const int rt = tile / ntc, c0 = (tile % ntc) * 8;
         const int r0 = r_first + rt * 8;
+        const cplx y0 = yn0, y1 = yn1;
+        {
+          const int tn = tile + nwarp;
+          if (tn < ntr * ntc) {
+            const int rn = r_first + (tn / ntc) * 8 + g, cn = (tn % ntc) * 8 + 2 * t4;
+            if (rn < mr) {
+              const cplx* ys = src + (size_t)rn * ld + p0;
+              if (cn < n) yn0 = ys[cn];
+              if (cn + 1 < n) yn1 = ys[cn + 1];
+            }
+          }
+        }
         ZTile acc = ztile_zero();
         const cplx* zt = Zs + rt * 64;
         warp_zgemm_8x8(
@@ -720,16 +746,9 @@ __global__ void __launch_bounds__(1024) k_lq(DqaDev d, int l) {
             [&](int kk, int col) { return (kk < pb && c0 + col < n) ? Vp[kk * npad + c0 + col] : cmk(0.0, 0.0); });
         const int r = r0 + g, c = c0 + 2 * t4;
         if (r < mr) {
-          const cplx* ys = src + (size_t)r * ld + p0;
           cplx* yd = wk + (size_t)r * ld + p0;
-          if (c < n) {
-            const cplx y = ys[c];
-            yd[c] = cmk(y.x - acc.r0, y.y - acc.i0);
-          }
-          if (c + 1 < n) {
-            const cplx y = ys[c + 1];
-            yd[c + 1] = cmk(y.x - acc.r1, y.y - acc.i1);
-          }
+          if (c < n) yd[c] = cmk(y0.x - acc.r0, y0.y - acc.i0);
+          if (c + 1 < n) yd[c + 1] = cmk(y1.x - acc.r1, y1.y - acc.i1);
         }
       }
       tl_trail += clock64() - tl2;

@@ -190,20 +190,56 @@ inline void run_block() {
   s.w_gen.assign(nw, 0);
   s.w_buf.resize(nw * 32);
   int remaining = s.nthreads;
+  // Scheduling: by default every pass runs all fibers in thread order (every warp advances one synchronisation point per
+  // pass, in lock step).  With DQA_EMUL_SEED=<n> the order of the WARPS is shuffled every pass and, now and then, a warp
+  // is held back for up to 255 passes while the others run until they block on it -- an adversarial schedule for
+  // kernels whose warps hand data to each other without a block barrier (a warp racing a whole round ahead of its
+  // neighbour is exactly what real hardware does and lock-step emulation hides).
+  static const char* seed_env = std::getenv("DQA_EMUL_SEED");
+  static unsigned long long rng = seed_env ? 0x9E3779B97F4A7C15ull * (unsigned long long)(std::atoll(seed_env) + 1) : 0ull;
+  auto next_rand = [&]() {
+    rng ^= rng << 13;
+    rng ^= rng >> 7;
+    rng ^= rng << 17;
+    return rng;
+  };
+  std::vector<int> worder(nw), hold(nw, 0);
+  for (int w = 0; w < nw; ++w) worder[w] = w;
+  int idle_passes = 0;
   while (remaining > 0) {
     long before = s.progress;
     int ran = 0;
-    for (int t = 0; t < s.nthreads; ++t) {
-      if (s.fibers[t].done) continue;
-      s.cur = t;
-      set_tid(t);
-      swapcontext(&s.sched, &s.fibers[t].ctx);
-      ran++;
-      if (s.fibers[t].done) remaining--, s.progress++;
+    if (seed_env)
+      for (int w = nw - 1; w > 0; --w) std::swap(worder[w], worder[next_rand() % (unsigned)(w + 1)]);
+    for (int wi = 0; wi < nw; ++wi) {
+      const int w = worder[wi];
+      if (seed_env) {
+        if (hold[w] > 0) {
+          hold[w]--;
+          continue;
+        }
+        if ((next_rand() & 63) == 0) {
+          hold[w] = (int)(next_rand() & 255);
+          continue;
+        }
+      }
+      for (int t = w * 32; t < s.nthreads && t < w * 32 + 32; ++t) {
+        if (s.fibers[t].done) continue;
+        s.cur = t;
+        set_tid(t);
+        swapcontext(&s.sched, &s.fibers[t].ctx);
+        ran++;
+        if (s.fibers[t].done) remaining--, s.progress++;
+      }
     }
     if (ran > 0 && s.progress == before) {
-      std::fprintf(stderr, "cuda_emul: deadlock (divergent barrier/shuffle) in block (%u,%u)\n", blockIdx_.x, blockIdx_.y);
-      std::abort();
+      // a warp spinning on a flag makes no "progress" by itself: only call it a deadlock when nothing moves for a long time
+      if (++idle_passes > (seed_env ? 4096 : 0)) {
+        std::fprintf(stderr, "cuda_emul: deadlock (divergent barrier/shuffle) in block (%u,%u)\n", blockIdx_.x, blockIdx_.y);
+        std::abort();
+      }
+    } else if (ran > 0) {
+      idle_passes = 0;
     }
   }
 }

@@ -102,3 +102,17 @@ def test_ops_dense_substep_and_energy(tenn_emul):
     os_.check_dense_substep_equals_reference(T)
     os_.check_energy_ext(T, o)
     os_.check_statevector(o)
+
+
+@pytest.mark.parametrize("seed", [1, 2])
+def test_adversarial_warp_schedule(seed):
+    """Same kernels with the emulator's warps scheduled in random order and randomly held back (DQA_EMUL_SEED): hand-offs
+    between warps that rely on lock-step scheduling instead of a barrier show up here as wrong results or a deadlock."""
+    import os
+    import subprocess
+    import sys
+
+    here = os.path.dirname(os.path.abspath(__file__))
+    env = dict(os.environ, DQA_EMUL_SEED=str(seed), OMP_NUM_THREADS="1")
+    r = subprocess.run([sys.executable, os.path.join(here, "emul", "adversarial_check.py")], env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]

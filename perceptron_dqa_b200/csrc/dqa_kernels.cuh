@@ -552,9 +552,10 @@ __global__ void __launch_bounds__(1024) k_lq(DqaDev d, int l) {
     const int pb = (k - p0) < pbmax ? (k - p0) : pbmax;
     const int n = Q - p0;  // panel columns p0..Q-1
     const cplx* src = (p0 == 0) ? th : wk;
-    for (int i = tid; i < pb * n; i += nt) {
-      const int c = i % n, r = i / n;
-      Vp[r * npad + c] = src[(size_t)(p0 + r) * ld + p0 + c];
+    for (int c = tid; c < n; c += nt) {  // row by row: independent loads, no integer division
+#pragma unroll
+      for (int r = 0; r < LQ_PB; ++r)
+        if (r < pb) Vp[r * npad + c] = src[(size_t)(p0 + r) * ld + p0 + c];
     }
     __syncthreads();
     tl_t += clock64() - tl0;  // panel load (reported as the "tmat" counter)

@@ -784,8 +784,14 @@ __global__ void __launch_bounds__(1024) k_lq(DqaDev d, int l) {
 // L lives in shared memory while (2chi)^2 complex fit next to two more CTAs' worth of headroom; beyond
 // that (chi > 56) the kernel iterates on the L2-resident copy in `lbuf` (same code, generic pointers).
 __host__ __device__ inline bool svd_l_in_smem(int chi) { return sizeof(cplx) * (size_t)(2 * chi) * (2 * chi) <= 200 * 1024; }
+// When L does not fit (chi > 56) its first svd_hyb_cols(chi) columns still live in shared memory and only the rest is
+// iterated on in L2 (chi = 64: 108 of 128 columns, so 71 % of the column pairs never leave shared memory).
+__host__ __device__ inline int svd_hyb_cols(int chi) {
+  return svd_l_in_smem(chi) ? 0 : (int)(((size_t)216 * 1024) / (sizeof(cplx) * (size_t)(2 * chi))) & ~3;
+}
 __host__ __device__ inline size_t svd_smem(int chi) {
-  return (svd_l_in_smem(chi) ? sizeof(cplx) * (size_t)(2 * chi) * (2 * chi) : 0) + sizeof(double) * (4 * chi + 8) + sizeof(int) * (2 * chi + 8);
+  return (svd_l_in_smem(chi) ? sizeof(cplx) * (size_t)(2 * chi) * (2 * chi) : sizeof(cplx) * (size_t)svd_hyb_cols(chi) * (2 * chi)) +
+         sizeof(double) * (4 * chi + 8) + sizeof(int) * (2 * chi + 8);
 }
 
 __device__ __forceinline__ void rr_pair(int n, int round, int idx, int& p, int& q) {
@@ -892,7 +898,9 @@ __global__ void __launch_bounds__(512) k_jacobi(DqaDev d, int l, int mu, int p_s
   cplx* lglob = d.lbuf + (size_t)inst * (size_t)(2 * chi) * (2 * chi);
   cplx* L;
   if (LSM) L = (cplx*)smraw; else L = lglob;
-  double* sig = (double*)(smraw + (lsm ? sizeof(cplx) * (size_t)(2 * chi) * (2 * chi) : 0));
+  const int cs = LSM ? 0 : svd_hyb_cols(chi);  // hybrid (not LSM): columns < cs are iterated on in shared memory, ld 2chi
+  cplx* Ls = (cplx*)smraw;
+  double* sig = (double*)(smraw + (lsm ? sizeof(cplx) * (size_t)(2 * chi) * (2 * chi) : sizeof(cplx) * (size_t)cs * (2 * chi)));
   double* ssorted = sig + 2 * chi;
   int* order = (int*)(ssorted + 2 * chi + 8);
   int* sh_i = order + 2 * chi;  // [0]=rotation count, [1]=n_chi, [2]=some rotated pair was above the quadratic threshold
@@ -907,8 +915,15 @@ __global__ void __launch_bounds__(512) k_jacobi(DqaDev d, int l, int mu, int p_s
       const int r = i % mr, c = i / mr;
       L[r + c * ldl] = lglob[r + c * (2 * chi)];
     }
+  } else {
+    const int kc = k < cs ? k : cs;
+    for (int i = tid; i < mr * kc; i += nt) {
+      const int r = i % mr, c = i / mr;
+      Ls[r + c * ldl] = lglob[r + c * ldl];
+    }
   }
   __syncthreads();
+  auto colp = [&](int j) -> cplx* { return (LSM ? L : (j < cs ? Ls : lglob)) + (size_t)j * ldl; };
 
   // Work decomposition: a warp is 4 groups of 8 lanes; one group owns one column pair per
   // pass (8 lanes x mr/8 rows each), so a warp orthogonalises 4 pairs per pass with 3-stage
@@ -926,7 +941,7 @@ __global__ void __launch_bounds__(512) k_jacobi(DqaDev d, int l, int mu, int p_s
       const int j = j0 + grp;
       double a = 0.0;
       if (j < k)
-        for (int r = li; r < mr; r += 8) a += cabs2(L[r + j * ldl]);
+        for (int r = li; r < mr; r += 8) a += cabs2(colp(j)[r]);
       a += __shfl_xor_sync(DQA_FULL, a, 4);
       a += __shfl_xor_sync(DQA_FULL, a, 2);
       a += __shfl_xor_sync(DQA_FULL, a, 1);
@@ -960,8 +975,8 @@ __global__ void __launch_bounds__(512) k_jacobi(DqaDev d, int l, int mu, int p_s
           b0 = nrm2[q];
         }
         if (act) {
-          const cplx* xp = L + p * ldl;
-          const cplx* xq = L + q * ldl;
+          const cplx* xp = colp(p);
+          const cplx* xq = colp(q);
           for (int r = li; r < mr; r += 8) g = cfmac(xq[r], xp[r], g);  // conj(xp) * xq
         }
         g.x += __shfl_xor_sync(DQA_FULL, g.x, 4);
@@ -1033,8 +1048,8 @@ __global__ void __launch_bounds__(512) k_jacobi(DqaDev d, int l, int mu, int p_s
           cph = cmk(__shfl_sync(DQA_FULL, rcph.x, src), __shfl_sync(DQA_FULL, rcph.y, src));
         }
         if (dr) {
-          cplx* xp = L + p * ldl;
-          cplx* xq = L + q * ldl;
+          cplx* xp = colp(p);
+          cplx* xq = colp(q);
           for (int r = li; r < mr; r += 8) {
             const cplx a_ = xp[r], b_ = xq[r];
             xp[r] = cfms(sph, b_, cscale(a_, c));   // c*xp - s e^{-i phi} xq
@@ -1056,6 +1071,14 @@ __global__ void __launch_bounds__(512) k_jacobi(DqaDev d, int l, int mu, int p_s
     __syncthreads();
   }
 
+  if (!LSM && cs > 0) {  // the tail reads the factor from one place: put the shared-memory columns back
+    const int kc = k < cs ? k : cs;
+    for (int i = tid; i < mr * kc; i += nt) {
+      const int r = i % mr, c = i / mr;
+      lglob[r + c * ldl] = Ls[r + c * ldl];
+    }
+    __syncthreads();
+  }
   jacobi_tail(d, inst, l, mu, p_step, L, ldl, mr, k, k, sig, ssorted, order, sh_i, bond, converged, sweeps, nrot_total);
 }
 

@@ -264,7 +264,7 @@ def test_bond_sweep_non_power_of_two(factory):
 
 def test_bond_sweep_above_32(factory):
     # chi in (32,56]: k_sector_qr<12>/<16> and the shared-memory-resident Jacobi kernel
-    ps.check_bond_sweep(factory, chis=(40, 48, 56), steps=2)
+    ps.check_bond_sweep(factory, chis=(40, 48, 56, 64), steps=2)
 
 
 def test_driver_class_matches_fixture():

@@ -118,6 +118,9 @@ __global__ void k_init_plus(DqaDev d) {
 // column with no block barrier at all (column j only needs reflectors j..0).
 // shared memory: M (2chi x chi, col-major; column k ends up holding reflector v_k) | tau | beta
 // ---------------------------------------------------------------------------------
+#ifndef SQR_TWO_UPTO
+#define SQR_TWO_UPTO 12  // largest slot count compiled for two CTAs per SM (12 slots spill at 85 registers and still gain 13 %)
+#endif
 #ifndef SQR_MINB
 #define SQR_MINB 3  // CTAs per SM the 8-slot sector-QR kernel is compiled for
 #endif
@@ -225,7 +228,7 @@ __device__ __forceinline__ void sqr_apply(cplx (&col)[MAXS], const cplx* vk, cpl
 }
 
 template <int MAXS>
-__global__ void __launch_bounds__(MAXS <= 8 ? 256 : (MAXS == 10 ? 320 : (MAXS == 12 ? 384 : 512)), MAXS <= 4 ? 4 : (MAXS <= 8 ? SQR_MINB : (MAXS == 10 ? 2 : 1))) k_sector_qr(DqaDev d, int n, int mu) {
+__global__ void __launch_bounds__(MAXS <= 8 ? 256 : (MAXS == 10 ? 320 : (MAXS == 12 ? 384 : 512)), MAXS <= 4 ? 4 : (MAXS <= 8 ? SQR_MINB : (MAXS <= SQR_TWO_UPTO ? 2 : 1))) k_sector_qr(DqaDev d, int n, int mu) {
   DQA_DYN_SMEM(smraw);
   const int y = blockIdx.x, inst = blockIdx.y;
   const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarp = nt >> 5;

@@ -91,6 +91,38 @@ def run_config(name, xi, P, dt, chi, steps, snap_at, sgn0fix=True, svd_driver="g
     return out
 
 
+def run_saturated_substep(name, xi, P, dt, chi, warm_substeps):
+    """One teacher-forced sub-step on a state whose bonds have reached chi: the reference's own sub-step functions are
+    applied `warm_substeps` times from |+> (no energy evaluations: the reference's compute_loss builds chi^4 tensors), then
+    the next sub-step is stored as (pre, post)."""
+    mod = ref_runner.load(sgn0fix=True, svd_driver="gesdd")
+    obj = mod.mydQA(xi, P=P, dt=dt, max_bond=chi)
+    obj.init_fourier()
+    t0 = time.time()
+    psi = [np.array([[[2**-0.5], [2**-0.5]]], dtype=np.complex128)] * obj.N
+    p = mu = 0
+    with ref_runner.quiet():
+        for _ in range(warm_substeps):
+            obj.pp = p
+            psi = reference_substep(mod, obj, [np.array(t) for t in psi], mu)
+            mu += 1
+            if mu == obj.N_xi:
+                # the mixer of the reference's single_step (dQA_mps.py:108-109)
+                beta = (1.0 - (p + 1) / P) * dt
+                psi = mod.apply_mpsmpo(psi, mod.PerceptronHamiltonian.make_Ux(obj.N, beta_p=beta))
+                mu, p = 0, p + 1
+        obj.pp = p
+        b0, f0 = pack_mps(psi)
+        post = reference_substep(mod, obj, [np.array(t) for t in psi], mu)
+        b1, f1 = pack_mps(post)
+    xi64 = np.asarray(xi).astype(np.int64)
+    out = {"xi": np.asarray(xi).astype(np.int8), "P": P, "dt": dt, "chi": chi, "steps": 0, "Uk_FT": obj.Uk_FT, "fxft": obj.fxft,
+           "hbit": ((1 - xi64) // 2).astype(np.uint8), "snap_index": np.array([(p, mu)], dtype=np.int32),
+           "snap0_pre_bonds": b0, "snap0_pre_flat": f0, "snap0_post_bonds": b1, "snap0_post_flat": f1}
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print(f"{name}: {warm_substeps} warm-up sub-steps in {time.time() - t0:.1f}s, bonds {b0.tolist()} -> {b1.tolist()}", flush=True)
+
+
 def main():
     which = sys.argv[1:] or ["n7", "c1", "c1_spread", "c2", "n15"]
     if "n7" in which:
@@ -127,6 +159,11 @@ def main():
         rng = np.random.default_rng(64)
         xi = (2 * rng.integers(0, 2, size=(4, 32)) - 1).astype(np.int8)
         run_config("n32_chi8_synthetic", xi, P=50, dt=1.0, chi=8, steps=3, snap_at={2: {0, 3}})
+    if "n14_chi64" in which:
+        # saturated bonds at the largest supported chi (the 2chi = 128-column SVD): synthetic iid +-1 patterns, default_rng(14)
+        rng = np.random.default_rng(14)
+        xi = (2 * rng.integers(0, 2, size=(int(os.environ.get("NXI", "8")), 14)) - 1).astype(np.int8)
+        run_saturated_substep("n14_chi64_saturated", xi, P=20, dt=1.0, chi=64, warm_substeps=int(os.environ.get("WARM", "32")))
     if "c3_16" in which:
         xi = np.load(os.path.join(DATA, "patterns_17-21.1.npy"))
         run_config("c3_n21_chi16", xi, P=100, dt=1.0, chi=16, steps=4, snap_at={3: {0, 16}})

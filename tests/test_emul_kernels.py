@@ -104,6 +104,12 @@ def test_ops_dense_substep_and_energy(tenn_emul):
     os_.check_statevector(o)
 
 
+def test_bond_64_kernels(factory):
+    # chi = 64: k_sector_qr<16> and the chi > 56 Jacobi kernel (bonds up to 43 here: all its columns are in shared memory;
+    # the saturated 128-column case, where 20 columns stay in global memory, is the GPU test on n14_chi64_saturated)
+    ps.check_teacher_forced(factory, "n12_chi64_untruncated", max_snaps=1)
+
+
 @pytest.mark.parametrize("seed", [1, 2])
 def test_adversarial_warp_schedule(seed):
     """Same kernels with the emulator's warps scheduled in random order and randomly held back (DQA_EMUL_SEED): hand-offs

@@ -262,6 +262,12 @@ def test_bond_sweep_non_power_of_two(factory):
     ps.check_bond_sweep(factory)
 
 
+def test_p1_saturated_chi64_substep(factory):
+    # bonds of 64 on both sides of the centre: the 128-column SVD (hybrid shared-memory / L2 Jacobi), k_sector_qr<16>,
+    # and the LQ of a 128 x 960 Theta, against the reference's own sub-step (tests/golden/n14_chi64_saturated.npz)
+    ps.check_teacher_forced(factory, "n14_chi64_saturated")
+
+
 def test_bond_sweep_above_32(factory):
     # chi in (32,56]: k_sector_qr<12>/<16> and the shared-memory-resident Jacobi kernel
     ps.check_bond_sweep(factory, chis=(40, 48, 56, 64), steps=2)

@@ -188,7 +188,7 @@ def check_small_edge_cases(factory, cases=None):
         assert not pl.status().any()
 
 
-def check_bond_sweep(factory, chis=(12, 20, 24, 28), n=12, n_xi=5, P=6, steps=3, dt=0.8):
+def check_bond_sweep(factory, chis=(12, 16, 20, 24, 28, 32), n=12, n_xi=5, P=6, steps=3, dt=0.8):
     """Bond dimensions that are not powers of two (column-pair counts that do not fill the Jacobi kernel's warps, odd
     numbers of LQ panels, ragged DMMA tiles): first steps of a run on iid patterns against the oracle run on the fly."""
     rng = np.random.default_rng(29)

@@ -164,6 +164,11 @@ def main():
         rng = np.random.default_rng(14)
         xi = (2 * rng.integers(0, 2, size=(int(os.environ.get("NXI", "8")), 14)) - 1).astype(np.int8)
         run_saturated_substep("n14_chi64_saturated", xi, P=20, dt=1.0, chi=64, warm_substeps=int(os.environ.get("WARM", "32")))
+    if "n12_chi48" in which:
+        # saturated bonds in the 12-slot sector-QR / shared-memory-resident Jacobi range (32 < chi <= 56), default_rng(48)
+        rng = np.random.default_rng(48)
+        xi = (2 * rng.integers(0, 2, size=(8, 12)) - 1).astype(np.int8)
+        run_saturated_substep("n12_chi48_saturated", xi, P=20, dt=1.0, chi=48, warm_substeps=32)
     if "c3_16" in which:
         xi = np.load(os.path.join(DATA, "patterns_17-21.1.npy"))
         run_config("c3_n21_chi16", xi, P=100, dt=1.0, chi=16, steps=4, snap_at={3: {0, 16}})

@@ -110,6 +110,11 @@ def test_bond_64_kernels(factory):
     ps.check_teacher_forced(factory, "n12_chi64_untruncated", max_snaps=1)
 
 
+def test_bond_48_saturated(factory):
+    # 32 < chi <= 56 at saturation: k_sector_qr<12>, blocked LQ with 96 rows, the shared-memory-resident k_jacobi
+    ps.check_teacher_forced(factory, "n12_chi48_saturated")
+
+
 @pytest.mark.parametrize("seed", [1, 2])
 def test_adversarial_warp_schedule(seed):
     """Same kernels with the emulator's warps scheduled in random order and randomly held back (DQA_EMUL_SEED): hand-offs

@@ -268,6 +268,11 @@ def test_p1_saturated_chi64_substep(factory):
     ps.check_teacher_forced(factory, "n14_chi64_saturated")
 
 
+def test_p1_saturated_chi48_substep(factory):
+    # bond 48 at the centre: 12-slot sector QR (two CTAs per SM, with register spills) and the shared-memory-resident Jacobi
+    ps.check_teacher_forced(factory, "n12_chi48_saturated")
+
+
 def test_bond_sweep_above_32(factory):
     # chi in (32,56]: k_sector_qr<12>/<16> and the shared-memory-resident Jacobi kernel
     ps.check_bond_sweep(factory, chis=(40, 48, 56, 64), steps=2)

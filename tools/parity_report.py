@@ -16,7 +16,7 @@ from perceptron_dqa_b200._lib import Plan  # noqa: E402
 fac = lambda N, n_xi, P, dt, chi, b: Plan(N, n_xi, P, dt, chi, batch=b)  # noqa: E731
 print("fixture                 N  chi substeps  max|1-F|   max|dSchmidt|  max|d eps|   bond dims equal")
 for name in ("n7_chi4", "n7_chi8_untruncated", "c1_n12_chi10", "n15_chi10", "c2_n21_chi10", "c3_n21_chi32",
-             "n12_chi64_untruncated", "n14_chi64_saturated", "n32_chi8_synthetic"):
+             "n12_chi48_saturated", "n12_chi64_untruncated", "n14_chi64_saturated", "n32_chi8_synthetic"):
     g = golden(name)
     pl = ps.make(fac, g)
     wf = ws = we = 0.0

@@ -52,7 +52,7 @@ def test_oracle_reproduces_reference_trajectory(name, steps):
     assert o.bd_monitor == g["bd_monitor"][: len(o.bd_monitor)].tolist()
 
 
-@pytest.mark.parametrize("name", CONFIGS)
+@pytest.mark.parametrize("name", CONFIGS + ["n12_chi48_saturated", "n14_chi64_saturated"])
 def test_oracle_substeps_teacher_forced(name):
     g = golden(name)
     o = O.OracleDQA(g["xi"], int(g["P"]), float(g["dt"]), int(g["chi"]), fast_loss=True)

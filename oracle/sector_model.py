@@ -137,8 +137,9 @@ def uz_diagonal(uk_col, n):
 
 
 def round_robin_pairs(n):
-    """The (n-1)-round tournament ordering the Jacobi kernel uses (n even after padding):
-    round r pairs position i with position n-1-i of the rotated ring."""
+    """The (n-1)-round tournament ordering of k_jacobi (bonds above 32; n even after padding): round r pairs position i
+    with position n-1-i of the rotated ring.  The systolic kernel for chi <= 32 (k_jacobi_sys) visits the same pairs in
+    the odd-even transposition order instead; both are cyclic orderings with the same fixed point, the SVD."""
     m = n + (n & 1)
     ring = list(range(m))
     rounds = []

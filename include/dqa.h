@@ -50,10 +50,16 @@ typedef struct dqa_config {
   int32_t batch;       /* independent realisations evolved by this handle */
   int32_t device;      /* CUDA device ordinal                             */
   int32_t max_sweeps;  /* Jacobi sweep cap (0 -> 30)                      */
-  int32_t reserved;
-  double dt;
+  int32_t n_tables;    /* Fourier tables (distinct dt values) in the batch; 0 -> 1 */
+  double dt;           /* dt of every instance (n_tables == 1)            */
   double cutoff;       /* 0 -> 1e-10 (lib/tenn.py:238); <0 -> no cutoff    */
   void* stream;        /* cudaStream_t, NULL = legacy default stream      */
+  /* truncation policy of svd_truncated / _trim_and_renorm_svd_result (lib/tenn.py:307-405).  policy_set = 0 keeps
+   * the values the reference hard-codes at its call site (lib/tenn.py:238): mode 4, renorm 2, absorb 1. */
+  int32_t policy_set;  /* 0: reference defaults; 1: take the three fields below verbatim */
+  int32_t cutoff_mode; /* 1 abs, 2 rel, 3 sum2, 4 rsum2, 5 sum1, 6 rsum1 (lib/tenn.py:317-345) */
+  int32_t renorm;      /* 0: kept values as they are; >0: rescaled to preserve their p-norm (lib/tenn.py:347-354) */
+  int32_t absorb;      /* where S goes: 1 = right, the only value compress_svd_normalized's sweep can use (DQA_ELIMIT otherwise) */
 } dqa_config;
 
 /* life cycle ---------------------------------------------------------------------- */
@@ -69,6 +75,12 @@ int dqa_set_patterns(dqa_t* h, const int8_t* xi);
 /* Tables of mydQA.init_fourier (dQA_mps.py:62-66), computed by the caller exactly as the
  * reference does: Uk_FT host complex128 [D][P], fxft host complex128 [D], D = N+1. */
 int dqa_set_fourier(dqa_t* h, const double* Uk_FT, const double* fxft);
+/* The same for a batch whose instances run different dt (the dt grid of benchmarker-mps.py:50-57 mapped onto the
+ * ensemble dimension): Uk_FT host complex128 [n_tables][D][P], one init_fourier table per distinct dt; fxft [D]
+ * (independent of dt); table_of_instance [batch]; dt_of_instance [batch] (the mixer angle (1-s_p)*dt, dQA_mps.py:88-89).
+ * n_tables must equal dqa_config.n_tables. */
+int dqa_set_fourier_tables(dqa_t* h, int n_tables, const double* Uk_FT, const double* fxft, const int32_t* table_of_instance,
+                           const double* dt_of_instance);
 /* Integer pattern-to-MPO tables, computed ON THE DEVICE, for the bit-exact check
  * (lib/dQA_utils.py:50-53,106): hbit [n_xi][N] u8, e [n_xi][N][2] i32, q [n_xi][N][2][D] i32.
  * Any output pointer may be NULL. */
@@ -114,6 +126,11 @@ int dqa_get_schmidt(dqa_t* h, int inst, int bond, double* s /* [2*chi] */, int* 
 int dqa_get_eps(dqa_t* h, double* eps /* [batch][P+1] complex */);
 int dqa_get_bd_monitor(dqa_t* h, int32_t* bd /* [batch][P*n_xi] */);
 int dqa_get_status(dqa_t* h, int32_t* status /* [batch] */);
+/* status words are sticky until a new state is loaded (dqa_reset_plus / dqa_set_mps / dqa_upload_state) or cleared here */
+int dqa_clear_status(dqa_t* h);
+/* relative discarded weight (sum of dropped s^2 / sum of all s^2) of the last truncation at every cut: w [N-1]
+ * (what _trim_and_renorm_svd_result, lib/tenn.py:347-354, renormalises away) */
+int dqa_get_truncation_error(dqa_t* h, int inst, double* w);
 /* [batch][16] u64: Jacobi rotations, Jacobi sweeps, SVDs, QR columns, and the FP64 flops executed by
  * the Householder LQ, the Jacobi iteration, the sector QRs and the theta GEMMs (exact loop counts),
  * then thread-0 clock cycles per phase and CTA counts of k_sector_qr (8..11) and k_lq (12..15). */

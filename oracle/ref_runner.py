@@ -1,6 +1,7 @@
 """TEST INFRASTRUCTURE ONLY -- run the reference's own files, unmodified, in complex128.
 
-Works only where /root/reference exists (the build container).  Used by
+Works where /root/reference exists (the build container) or where oracle/make_ref.py has staged the four
+hot-path files into oracle/_ref/ (the GPU box: bench.py's CPU legs only).  Used by
 oracle/make_golden.py to produce the fixtures under tests/golden/ and by
 tests/test_oracle_vs_reference.py to pin oracle/dqa_oracle.py (the travelling
 numpy restatement) against the real reference.  Never imported by the product.
@@ -14,8 +15,22 @@ import io
 import os
 import sys
 
-REFERENCE_ROOT = os.environ.get("DQA_REFERENCE_ROOT", "/root/reference")
-_SHIM = os.path.join(os.path.dirname(os.path.abspath(__file__)), "shim")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_STAGED = os.path.join(_HERE, "_ref")  # verbatim copies made by oracle/make_ref.py (git-ignored, travels with gpurun)
+
+
+def _pick_root():
+    env = os.environ.get("DQA_REFERENCE_ROOT")
+    if env:
+        return env
+    for cand in ("/root/reference", _STAGED):
+        if os.path.isfile(os.path.join(cand, "dQA_mps.py")):
+            return cand
+    return "/root/reference"
+
+
+REFERENCE_ROOT = _pick_root()
+_SHIM = os.path.join(_HERE, "shim")
 
 
 def available():

@@ -89,7 +89,7 @@ def next_theta(c, n, nbit, R, Qb):
     return th.reshape(2 * cl, tot_out)
 
 
-def apply_pattern_sector(psi, u, nbit, chi, cutoff=1e-10, svd=None, stats=None):
+def apply_pattern_sector(psi, u, nbit, chi, cutoff=1e-10, svd=None, stats=None, cutoff_mode=4, renorm=2):
     """One sub-step (U_z^mu, canonise, truncate) in the sector representation.
 
     psi   list of (b_n,2,b_{n+1}) complex128 site tensors
@@ -103,7 +103,7 @@ def apply_pattern_sector(psi, u, nbit, chi, cutoff=1e-10, svd=None, stats=None):
     cl = 1
     for l in range(n_sites - 1):
         uu, s, vh = (svd or np.linalg.svd)(th, full_matrices=False)
-        n_chi, scale = trim_rule(s, cutoff=cutoff, cutoff_mode=4, max_bond=chi, renorm=2)
+        n_chi, scale = trim_rule(s, cutoff=cutoff, cutoff_mode=cutoff_mode, max_bond=chi, renorm=renorm)
         if stats is not None:
             stats.append((l, th.shape, s.copy(), n_chi))
         uk = uu[:, :n_chi]

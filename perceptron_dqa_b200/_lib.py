@@ -30,8 +30,9 @@ class DqaNumericError(DqaError):
 class dqa_config(C.Structure):
     _fields_ = [
         ("N", C.c_int32), ("n_xi", C.c_int32), ("P", C.c_int32), ("chi", C.c_int32),
-        ("batch", C.c_int32), ("device", C.c_int32), ("max_sweeps", C.c_int32), ("reserved", C.c_int32),
+        ("batch", C.c_int32), ("device", C.c_int32), ("max_sweeps", C.c_int32), ("n_tables", C.c_int32),
         ("dt", C.c_double), ("cutoff", C.c_double), ("stream", C.c_void_p),
+        ("policy_set", C.c_int32), ("cutoff_mode", C.c_int32), ("renorm", C.c_int32), ("absorb", C.c_int32),
     ]
 
 
@@ -44,6 +45,9 @@ _SIGS = {
     "dqa_bind_workspace": ([_P, _P, C.c_size_t], C.c_int),
     "dqa_set_patterns": ([_P, _P], C.c_int),
     "dqa_set_fourier": ([_P, _P, _P], C.c_int),
+    "dqa_set_fourier_tables": ([_P, C.c_int, _P, _P, _P, _P], C.c_int),
+    "dqa_clear_status": ([_P], C.c_int),
+    "dqa_get_truncation_error": ([_P, C.c_int, _P], C.c_int),
     "dqa_get_index_tensors": ([_P, C.c_int, _P, _P, _P], C.c_int),
     "dqa_reset_plus": ([_P], C.c_int),
     "dqa_step": ([_P, C.c_int], C.c_int),
@@ -132,12 +136,18 @@ class Plan:
     """One dqa_t*: N sites, n_xi patterns, P steps, bond chi, `batch` realisations on one GPU."""
 
     def __init__(self, N, n_xi, P, dt, chi, batch=1, device=0, cutoff=0.0, max_sweeps=0, stream=None,
-                 lib=None, workspace=None):
+                 lib=None, workspace=None, n_tables=1, cutoff_mode=None, renorm=None, absorb=None):
+        """cutoff_mode / renorm / absorb: the truncation policy of lib/tenn.py:238 (None = the reference's
+        hard-coded 4 / 2 / 1); n_tables > 1: instances with different dt (set_fourier_tables)."""
         self.lib = lib or load()
         self.N, self.n_xi, self.P, self.dt, self.chi, self.batch, self.device = N, n_xi, P, dt, chi, batch, device
         self.D = N + 1
+        self.n_tables = n_tables
+        policy = not (cutoff_mode is None and renorm is None and absorb is None)
         cfg = dqa_config(N=N, n_xi=n_xi, P=P, chi=chi, batch=batch, device=device, max_sweeps=max_sweeps,
-                         reserved=0, dt=dt, cutoff=cutoff, stream=stream)
+                         n_tables=n_tables, dt=dt, cutoff=cutoff, stream=stream, policy_set=int(policy),
+                         cutoff_mode=4 if cutoff_mode is None else int(cutoff_mode),
+                         renorm=2 if renorm is None else int(renorm), absorb=1 if absorb is None else int(absorb))
         self._h = _P()
         rc = self.lib.dqa_create(C.byref(self._h), C.byref(cfg))
         if rc != 0:
@@ -179,6 +189,16 @@ class Plan:
         fx = np.ascontiguousarray(fxft, dtype=np.complex128)
         assert uk.shape == (self.D, self.P) and fx.shape == (self.D,)
         self._ck(self.lib.dqa_set_fourier(self._h, _ptr(uk), _ptr(fx)))
+
+    def set_fourier_tables(self, uk_fts, fxft, table_of_instance, dt_of_instance):
+        """uk_fts (n_tables, D, P): one init_fourier table per distinct dt; instance b uses table_of_instance[b]."""
+        uk = np.ascontiguousarray(uk_fts, dtype=np.complex128)
+        fx = np.ascontiguousarray(fxft, dtype=np.complex128)
+        tab = np.ascontiguousarray(table_of_instance, dtype=np.int32)
+        dts = np.ascontiguousarray(dt_of_instance, dtype=np.float64)
+        assert uk.shape == (self.n_tables, self.D, self.P) and fx.shape == (self.D,)
+        assert tab.shape == (self.batch,) and dts.shape == (self.batch,)
+        self._ck(self.lib.dqa_set_fourier_tables(self._h, self.n_tables, _ptr(uk), _ptr(fx), _ptr(tab), _ptr(dts)))
 
     def index_tensors(self, inst=0):
         hbit = np.empty((self.n_xi, self.N), dtype=np.uint8)
@@ -286,6 +306,15 @@ class Plan:
     def status(self):
         out = np.empty(self.batch, dtype=np.int32)
         self._ck(self.lib.dqa_get_status(self._h, _ptr(out)))
+        return out
+
+    def clear_status(self):
+        self._ck(self.lib.dqa_clear_status(self._h))
+
+    def truncation_error(self, inst=0):
+        """relative discarded weight of the last truncation at every cut (N-1 values)"""
+        out = np.empty(self.N - 1, dtype=np.float64)
+        self._ck(self.lib.dqa_get_truncation_error(self._h, inst, _ptr(out)))
         return out
 
     def counters(self, reset=False):

@@ -54,6 +54,19 @@ struct dqa_handle {
   long long launches;
 };
 
+// A handle lives on cfg.device: every entry point makes that device current for its own duration and
+// restores the caller's (and torch's) current device on exit.
+struct DevGuard {
+  int prev = -1;
+  bool switched = false;
+  explicit DevGuard(int dev) {
+    if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) switched = (cudaSetDevice(dev) == cudaSuccess);
+  }
+  ~DevGuard() {
+    if (switched) cudaSetDevice(prev);
+  }
+};
+
 static int fail(const dqa_t* h, int code, const char* fmt, ...) {
   va_list ap;
   va_start(ap, fmt);
@@ -95,7 +108,9 @@ static void carve(const dqa_config& c, DqaDev& d, Aux& aux, char* base, size_t* 
   d.mps = cv.take<cplx>(B * N * 2 * chi * chi);
   d.bond = cv.take<int>(B * (N + 1));
   d.hbit = cv.take<uint8_t>(B * nx * N);
-  d.uz = cv.take<cplx>(P * D);
+  d.uz = cv.take<cplx>((size_t)d.ntab * P * D);
+  d.tab = cv.take<int>(B);
+  d.dtv = cv.take<double>(B);
   d.gk = cv.take<cplx>(D);
   d.phase = cv.take<cplx>(D);
   d.rbuf = cv.take<cplx>(B * 2 * d.smax * chi * chi);
@@ -109,6 +124,8 @@ static void carve(const dqa_config& c, DqaDev& d, Aux& aux, char* base, size_t* 
   d.nsv = cv.take<int>(B * N);
   d.tmk = cv.take<cplx>(B * nx * d.kh);
   d.eps = cv.take<cplx>(B * (P + 1));
+  d.escratch = cv.take<cplx>(B);
+  d.discw = cv.take<double>(B * N);
   d.bdmon = cv.take<int>(B * P * nx);
   d.status = cv.take<int>(B);
   d.counters = cv.take<unsigned long long>(B * DQA_NCNT);
@@ -130,6 +147,12 @@ extern "C" int dqa_create(dqa_t** out, const dqa_config* cfg) {
   if (c.max_sweeps <= 0) c.max_sweeps = 30;
   if (c.cutoff == 0.0) c.cutoff = 1e-10;
   if (c.cutoff < 0.0) c.cutoff = 0.0;
+  if (!c.policy_set) {  // the reference's hard-coded call site, lib/tenn.py:238
+    c.cutoff_mode = 4;
+    c.renorm = 2;
+    c.absorb = 1;
+  }
+  if (c.n_tables <= 0) c.n_tables = 1;
   *out = h;  // returned even on error so the message can be read; caller destroys it
   if (c.N < 2 || c.n_xi < 1 || c.P < 1 || c.chi < 1 || c.batch < 1) return fail(h, DQA_EINVAL, "N>=2, n_xi>=1, P>=1, chi>=1, batch>=1 required");
   if (c.N > 254) return fail(h, DQA_ELIMIT, "N=%d > 254 not supported", c.N);
@@ -137,6 +160,13 @@ extern "C" int dqa_create(dqa_t** out, const dqa_config* cfg) {
       false)
     return fail(h, DQA_ELIMIT, "chi=%d at N=%d needs more than 227 KB of shared memory per CTA in this build (chi <= 64, and chi*(N+1) bounded by the LQ panel)", c.chi, c.N);
   if (c.chi > 64) return fail(h, DQA_ELIMIT, "chi=%d > 64 not supported", c.chi);
+  if (c.cutoff_mode < 1 || c.cutoff_mode > 6) return fail(h, DQA_EINVAL, "cutoff_mode must be 1..6 (lib/tenn.py:317-345)");
+  if (c.renorm < 0) return fail(h, DQA_EINVAL, "renorm must be >= 0");
+  if (c.renorm > 0 && c.cutoff_mode < 3) return fail(h, DQA_EINVAL, "renorm needs a cumulative cutoff mode (3..6), as in lib/tenn.py:347-354");
+  if (c.absorb != 1)
+    return fail(h, DQA_ELIMIT, "absorb=%d: the left-to-right sweep of compress_svd_normalized absorbs to the right (lib/tenn.py:238); "
+                "other values are served by the op-level dqa_op_svd_truncated", c.absorb);
+  if (c.n_tables > c.batch) return fail(h, DQA_EINVAL, "n_tables > batch");
   h->stream = (cudaStream_t)c.stream;
   h->ws = nullptr;
   h->ws_bytes = 0;
@@ -174,6 +204,9 @@ extern "C" int dqa_create(dqa_t** out, const dqa_config* cfg) {
   d.kh = d.D / 2 + 1;
   d.max_sweeps = c.max_sweeps;
   d.cutoff = c.cutoff;
+  d.cutoff_mode = c.cutoff_mode;
+  d.renorm = c.renorm;
+  d.ntab = c.n_tables;
   {
     const char* env = getenv("DQA_JAC_QUAD");  // relative threshold, default 1e-10; 0 disables the shortcut
     const double q = env ? atof(env) : 1e-10;
@@ -215,33 +248,29 @@ extern "C" int dqa_create(dqa_t** out, const dqa_config* cfg) {
     const char* env = getenv("DQA_JAC_SYS");  // 0: use the shared-memory-resident Jacobi for every chi
     h->jac_sys = !(env && atoi(env) == 0);
   }
-  CK(cudaSetDevice(c.device));
-  CK(cudaFuncSetAttribute(k_sector_qr<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sector_qr_smem(c.chi)));
-  CK(cudaFuncSetAttribute(k_sector_qr<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sector_qr_smem(c.chi)));
-  CK(cudaFuncSetAttribute(k_sector_qr<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sector_qr_smem(c.chi)));
-  CK(cudaFuncSetAttribute(k_sector_qr<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sector_qr_smem(c.chi)));
-  CK(cudaFuncSetAttribute(k_sector_qr<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sector_qr_smem(c.chi)));
-  CK(cudaFuncSetAttribute(k_sector_qr<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sector_qr_smem(c.chi)));
-  CK(cudaFuncSetAttribute(k_sector_qr<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sector_qr_smem(c.chi)));
-  CK(cudaFuncSetAttribute(k_sector_qr<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sector_qr_smem(c.chi)));
-  CK(cudaFuncSetAttribute(KJ_0S, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)svd_smem(c.chi)));
-  CK(cudaFuncSetAttribute(KJ_0G, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)svd_smem(c.chi)));
-  if (c.chi <= 32) {
-    CK(cudaFuncSetAttribute(KJ_Y2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)svd_smem(c.chi)));
-    CK(cudaFuncSetAttribute(KJ_Y3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)svd_smem(c.chi)));
-    CK(cudaFuncSetAttribute(KJ_Y4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)svd_smem(c.chi)));
-    CK(cudaFuncSetAttribute(KJ_Y6, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)svd_smem(c.chi)));
-    CK(cudaFuncSetAttribute(KJ_Y8, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)svd_smem(c.chi)));
+  DevGuard guard(c.device);
+  {
+    int cur = -1;
+    CK(cudaGetDevice(&cur));
+    if (cur != c.device) CK(cudaSetDevice(c.device));  // surfaces an invalid ordinal; the guard restores the caller's device
   }
-  CK(cudaFuncSetAttribute(k_lq, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lq_smem(h->dev.qmax, c.chi, h->dev.lq_pb)));
-  CK(cudaFuncSetAttribute(KE_1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)energy_smem(c.chi)));
-  CK(cudaFuncSetAttribute(KE_2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)energy_smem(c.chi)));
-  CK(cudaFuncSetAttribute(k_theta, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)theta_smem(c.chi)));
+  // The opt-in limit is a property of the (process-global) kernel, not of this handle: always raise it to the device
+  // maximum, so a later plan with a smaller chi can never lower it under a live plan's launches.
+  int smem_optin = 0;
+  CK(cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, c.device));
+#define DQA_OPTIN(f) CK(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin))
+  DQA_OPTIN(k_sector_qr<2>); DQA_OPTIN(k_sector_qr<3>); DQA_OPTIN(k_sector_qr<4>); DQA_OPTIN(k_sector_qr<6>);
+  DQA_OPTIN(k_sector_qr<8>); DQA_OPTIN(k_sector_qr<10>); DQA_OPTIN(k_sector_qr<12>); DQA_OPTIN(k_sector_qr<16>);
+  DQA_OPTIN(KJ_0S); DQA_OPTIN(KJ_0G);
+  DQA_OPTIN(KJ_Y2); DQA_OPTIN(KJ_Y3); DQA_OPTIN(KJ_Y4); DQA_OPTIN(KJ_Y6); DQA_OPTIN(KJ_Y8);
+  DQA_OPTIN(k_lq); DQA_OPTIN(KE_1); DQA_OPTIN(KE_2); DQA_OPTIN(k_theta);
+#undef DQA_OPTIN
   return DQA_OK;
 }
 
 extern "C" void dqa_destroy(dqa_t* h) {
   if (!h) return;
+  DevGuard guard_(h->cfg.device);
   for (auto& e : h->evs) {
     cudaEventDestroy(e.a);
     cudaEventDestroy(e.b);
@@ -261,6 +290,7 @@ extern "C" int dqa_workspace_bytes(const dqa_t* h, size_t* bytes) {
 
 extern "C" int dqa_bind_workspace(dqa_t* h, void* p, size_t bytes) {
   if (!h || !p) return DQA_EINVAL;
+  DevGuard guard_(h->cfg.device);
   size_t need = 0;
   DqaDev tmp = h->dev;
   Aux aux;
@@ -280,6 +310,7 @@ extern "C" int dqa_bind_workspace(dqa_t* h, void* p, size_t bytes) {
 
 #define NEED_WS() \
   if (!h) return DQA_EINVAL; \
+  DevGuard guard_(h->cfg.device); \
   if (!h->ws) return fail(h, DQA_ESTATE, "bind a workspace first")
 
 extern "C" int dqa_set_patterns(dqa_t* h, const int8_t* xi) {
@@ -316,23 +347,14 @@ extern "C" int dqa_get_index_tensors(dqa_t* h, int inst, uint8_t* hbit, int32_t*
   return DQA_OK;
 }
 
-extern "C" int dqa_set_fourier(dqa_t* h, const double* uk_ft, const double* fxft) {
-  NEED_WS();
-  if (!uk_ft || !fxft) return DQA_EINVAL;
+// u_p(x) = (1/sqrt D) sum_k Uk_FT[k,p] exp(2 pi i k x / D): the diagonal of the Fourier MPO U_z
+// (lib/dQA_utils.py:46-59, product over the N sites of the per-site coefficient and phases).
+static void uz_from_ukft(const std::complex<double>* uk, int D, int P, std::complex<double>* uz) {
   typedef std::complex<double> cd;
-  const int D = h->dev.D, P = h->cfg.P;
-  const cd* uk = reinterpret_cast<const cd*>(uk_ft);
-  const cd* fx = reinterpret_cast<const cd*>(fxft);
-  // u_p(x) = (1/sqrt D) sum_k Uk_FT[k,p] exp(2 pi i k x / D): the diagonal of the Fourier MPO
-  // U_z (lib/dQA_utils.py:46-59, product over the N sites of the per-site coefficient and phases).
-  std::vector<cd> w(D), uz((size_t)P * D), gk(D), ph(D);
+  std::vector<cd> w(D);
   for (int k = 0; k < D; ++k) {
     const double ang = 2.0 * M_PI * k / D;
     w[k] = cd(std::cos(ang), std::sin(ang));
-    // phase table of the energy sweep: exp(i*(pi/D)*k*e) with e = 2 (lib/dQA_utils.py:106)
-    const double a2 = (M_PI / D) * k * 2.0;
-    ph[k] = cd(std::cos(a2), std::sin(a2));
-    gk[k] = fx[k] / std::sqrt((double)D);
   }
   const double rs = 1.0 / std::sqrt((double)D);
   for (int p = 0; p < P; ++p)
@@ -341,12 +363,53 @@ extern "C" int dqa_set_fourier(dqa_t* h, const double* uk_ft, const double* fxft
       for (int k = 0; k < D; ++k) acc += uk[(size_t)k * P + p] * w[(int)(((long)k * x) % D)];
       uz[(size_t)p * D + x] = acc * rs;
     }
+}
+
+static int set_fourier_impl(dqa_t* h, int ntab, const double* uk_ft, const double* fxft, const int32_t* tab, const double* dts) {
+  typedef std::complex<double> cd;
+  const int D = h->dev.D, P = h->cfg.P, B = h->cfg.batch;
+  const cd* uk = reinterpret_cast<const cd*>(uk_ft);
+  const cd* fx = reinterpret_cast<const cd*>(fxft);
+  std::vector<cd> uz((size_t)ntab * P * D), gk(D), ph(D);
+  for (int k = 0; k < D; ++k) {
+    // phase table of the energy sweep: exp(i*(pi/D)*k*e) with e = 2 (lib/dQA_utils.py:106)
+    const double a2 = (M_PI / D) * k * 2.0;
+    ph[k] = cd(std::cos(a2), std::sin(a2));
+    gk[k] = fx[k] / std::sqrt((double)D);
+  }
+  for (int t = 0; t < ntab; ++t) uz_from_ukft(uk + (size_t)t * D * P, D, P, uz.data() + (size_t)t * P * D);
+  std::vector<int> tb(B, 0);
+  std::vector<double> dv(B, h->cfg.dt);
+  for (int b = 0; b < B; ++b) {
+    if (tab) {
+      if (tab[b] < 0 || tab[b] >= ntab) return fail(h, DQA_EINVAL, "instance %d: table %d out of range", b, tab[b]);
+      tb[b] = tab[b];
+    }
+    if (dts) dv[b] = dts[b];
+  }
   CK(cudaMemcpyAsync(const_cast<cplx*>(h->dev.uz), uz.data(), sizeof(cd) * uz.size(), cudaMemcpyHostToDevice, h->stream));
   CK(cudaMemcpyAsync(const_cast<cplx*>(h->dev.gk), gk.data(), sizeof(cd) * D, cudaMemcpyHostToDevice, h->stream));
   CK(cudaMemcpyAsync(const_cast<cplx*>(h->dev.phase), ph.data(), sizeof(cd) * D, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(const_cast<int*>(h->dev.tab), tb.data(), sizeof(int) * B, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(const_cast<double*>(h->dev.dtv), dv.data(), sizeof(double) * B, cudaMemcpyHostToDevice, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   h->have_fourier = true;
   return DQA_OK;
+}
+
+extern "C" int dqa_set_fourier(dqa_t* h, const double* uk_ft, const double* fxft) {
+  NEED_WS();
+  if (!uk_ft || !fxft) return DQA_EINVAL;
+  if (h->dev.ntab != 1) return fail(h, DQA_ESTATE, "plan was created with n_tables=%d: use dqa_set_fourier_tables", h->dev.ntab);
+  return set_fourier_impl(h, 1, uk_ft, fxft, nullptr, nullptr);
+}
+
+extern "C" int dqa_set_fourier_tables(dqa_t* h, int n_tables, const double* uk_ft, const double* fxft, const int32_t* table_of_instance,
+                                      const double* dt_of_instance) {
+  NEED_WS();
+  if (!uk_ft || !fxft || !table_of_instance || !dt_of_instance) return DQA_EINVAL;
+  if (n_tables != h->dev.ntab) return fail(h, DQA_EINVAL, "n_tables=%d but the plan was created for %d", n_tables, h->dev.ntab);
+  return set_fourier_impl(h, n_tables, uk_ft, fxft, table_of_instance, dt_of_instance);
 }
 
 // ---- profiling helpers ---------------------------------------------------------------
@@ -377,6 +440,7 @@ extern "C" int dqa_profile_begin(dqa_t* h) {
 
 extern "C" int dqa_profile_end(dqa_t* h, double* ms, int64_t* launches) {
   if (!h || !ms || !launches) return DQA_EINVAL;
+  DevGuard guard_(h->cfg.device);
   CK(cudaStreamSynchronize(h->stream));
   for (int f = 0; f < DQA_NFAM; ++f) ms[f] = 0.0, launches[f] = 0;
   for (size_t i = 0; i < h->ev_used; ++i) {
@@ -444,12 +508,14 @@ static int launch_truncate(dqa_t* h, int p, int mu) {
   return DQA_OK;
 }
 
+// slot >= 0: eps trace slot; slot < 0: the scratch vector read by dqa_energy
 static int launch_energy(dqa_t* h, int slot) {
   const DqaDev& d = h->dev;
   prof_a(h, 4);
   if (d.chi > 16) HL(KE_2, dim3(d.kh, d.n_xi, d.batch), dim3(h->t_energy), energy_smem(d.chi), h->stream, d);
   else HL(KE_1, dim3(d.kh, d.n_xi, d.batch), dim3(h->t_energy), energy_smem(d.chi), h->stream, d);
-  HL(k_energy_reduce, dim3(d.batch), dim3(32), 0, h->stream, d, slot);
+  if (slot >= 0) HL(k_energy_reduce, dim3(d.batch), dim3(32), 0, h->stream, d, d.eps + slot, (size_t)(d.P + 1));
+  else HL(k_energy_reduce, dim3(d.batch), dim3(32), 0, h->stream, d, d.escratch, (size_t)1);
   prof_b(h);
   CK(cudaGetLastError());
   return DQA_OK;
@@ -499,14 +565,18 @@ extern "C" int dqa_apply_pattern(dqa_t* h, int p, int mu) {
   return launch_truncate(h, p, mu);
 }
 
-extern "C" int dqa_apply_ux(dqa_t* h, double beta) {
-  NEED_READY();
+static int launch_mixer(dqa_t* h, double beta, double one_minus_s, bool per_inst) {
   const DqaDev& d = h->dev;
   prof_a(h, 3);
-  HL(k_mixer, dim3(d.N, d.batch), dim3(128), 0, h->stream, d, std::cos(beta), std::sin(beta));
+  HL(k_mixer, dim3(d.N, d.batch), dim3(128), 0, h->stream, d, std::cos(beta), std::sin(beta), one_minus_s, per_inst ? 1 : 0);
   prof_b(h);
   CK(cudaGetLastError());
   return DQA_OK;
+}
+
+extern "C" int dqa_apply_ux(dqa_t* h, double beta) {
+  NEED_READY();
+  return launch_mixer(h, beta, 0.0, false);
 }
 
 static int check_status(dqa_t* h) {
@@ -535,7 +605,7 @@ static int step_impl(dqa_t* h, int nsteps, bool check) {
       rc = launch_truncate(h, p, mu);
       if (rc) return rc;
     }
-    int rc = dqa_apply_ux(h, beta);
+    int rc = launch_mixer(h, beta, 1.0 - s_p, h->dev.ntab > 1);  // several tables: beta = (1 - s_p) * dt of each instance
     if (rc) return rc;
     rc = launch_energy(h, p + 1);
     if (rc) return rc;
@@ -547,23 +617,11 @@ static int step_impl(dqa_t* h, int nsteps, bool check) {
 extern "C" int dqa_energy(dqa_t* h, double* eps) {
   NEED_READY();
   if (!eps) return DQA_EINVAL;
-  // slot P of the trace doubles as scratch only when the run is not finished; use a
-  // dedicated reduce into tmk-adjacent storage instead: reuse eps slot pp (it is rewritten by
-  // the step that owns it), then restore.
-  const DqaDev& d = h->dev;
-  std::vector<std::complex<double>> keep(d.batch), got(d.batch);
-  const int slot = h->pp;
-  for (int b = 0; b < d.batch; ++b)
-    CK(cudaMemcpyAsync(&keep[b], d.eps + (size_t)b * (d.P + 1) + slot, sizeof(cplx), cudaMemcpyDeviceToHost, h->stream));
-  int rc = launch_energy(h, slot);
+  // reduced into a scratch vector of its own (the eps trace is never touched), fetched with one contiguous copy
+  int rc = launch_energy(h, -1);
   if (rc) return rc;
-  for (int b = 0; b < d.batch; ++b)
-    CK(cudaMemcpyAsync(&got[b], d.eps + (size_t)b * (d.P + 1) + slot, sizeof(cplx), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(eps, h->dev.escratch, sizeof(cplx) * (size_t)h->dev.batch, cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
-  for (int b = 0; b < d.batch; ++b)
-    CK(cudaMemcpyAsync(d.eps + (size_t)b * (d.P + 1) + slot, &keep[b], sizeof(cplx), cudaMemcpyHostToDevice, h->stream));
-  CK(cudaStreamSynchronize(h->stream));
-  memcpy(eps, got.data(), sizeof(cplx) * d.batch);
   return DQA_OK;
 }
 
@@ -619,6 +677,7 @@ extern "C" int dqa_set_mps(dqa_t* h, int inst, int site, const double* buf, int 
   int b[2] = {l, r};
   CK(cudaMemcpyAsync(h->dev.mps + ((size_t)inst * N + site) * 2 * chi * chi, pad.data(), sizeof(cplx) * pad.size(), cudaMemcpyHostToDevice, h->stream));
   CK(cudaMemcpyAsync(h->dev.bond + (size_t)inst * (N + 1) + site, b, sizeof(int) * 2, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemsetAsync(h->dev.status + inst, 0, sizeof(int), h->stream));  // a freshly loaded state starts healthy
   CK(cudaStreamSynchronize(h->stream));
   h->have_state = true;
   return DQA_OK;
@@ -655,6 +714,18 @@ extern "C" int dqa_get_status(dqa_t* h, int32_t* st) {
   CK(cudaStreamSynchronize(h->stream));
   return DQA_OK;
 }
+extern "C" int dqa_clear_status(dqa_t* h) {
+  NEED_WS();
+  CK(cudaMemsetAsync(h->dev.status, 0, sizeof(int) * (size_t)h->cfg.batch, h->stream));
+  return DQA_OK;
+}
+extern "C" int dqa_get_truncation_error(dqa_t* h, int inst, double* w) {
+  NEED_WS();
+  if (!w || inst < 0 || inst >= h->cfg.batch) return DQA_EINVAL;
+  CK(cudaMemcpyAsync(w, h->dev.discw + (size_t)inst * h->cfg.N, sizeof(double) * (size_t)(h->cfg.N - 1), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return DQA_OK;
+}
 extern "C" int dqa_get_counters(dqa_t* h, uint64_t* c, int reset) {
   NEED_WS();
   if (!c) return DQA_EINVAL;
@@ -687,6 +758,7 @@ extern "C" int dqa_upload_state(dqa_t* h, const void* host) {
   const size_t nm = B * N * 2 * chi * chi * sizeof(cplx), nb = B * (N + 1) * sizeof(int);
   CK(cudaMemcpyAsync(h->dev.mps, host, nm, cudaMemcpyHostToDevice, h->stream));
   CK(cudaMemcpyAsync(h->dev.bond, (const char*)host + nm, nb, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemsetAsync(h->dev.status, 0, sizeof(int) * B, h->stream));  // a freshly loaded state starts healthy
   h->have_state = true;
   return DQA_OK;
 }
@@ -697,6 +769,7 @@ extern "C" int dqa_get_launch_count(const dqa_t* h, int64_t* n) {
 }
 extern "C" int dqa_sync(dqa_t* h) {
   if (!h) return DQA_EINVAL;
+  DevGuard guard_(h->cfg.device);
   CK(cudaStreamSynchronize(h->stream));
   return DQA_OK;
 }

@@ -183,12 +183,17 @@ struct DqaDev {
   int nsec_total;  // number of (site, sector) Q blocks per instance
   int kh;          // D/2+1: independent Fourier modes of the energy sweep
   int max_sweeps;
+  int cutoff_mode;  // 1 abs, 2 rel, 3 sum2, 4 rsum2, 5 sum1, 6 rsum1 (lib/tenn.py:317-345); the reference hard-codes 4
+  int renorm;       // 0: kept values not rescaled; > 0: rescaled so their p-norm is preserved (lib/tenn.py:347-354); reference: 2
+  int ntab;         // number of Fourier tables (1 unless instances run different dt)
   double cutoff;
   double jac_quad2;  // (relative off-diagonal)^2 below which a rotated pair counts as already converged (0: always run the checking sweep)
   cplx* mps;              // [batch][N][chi*2*chi]   site (a,s,c) at (a*2+s)*chi + c
   int* bond;              // [batch][N+1]
   const uint8_t* hbit;    // [batch][n_xi][N]        (1 - xi)/2
-  const cplx* uz;         // [P][D]                  u_p(x) = exp(-i gamma_p f(x))
+  const cplx* uz;         // [ntab][P][D]            u_p(x) = exp(-i gamma_p f(x)), one table per distinct dt
+  const int* tab;         // [batch]                 Fourier table of each instance
+  const double* dtv;      // [batch]                 dt of each instance (mixer angle), only read when ntab > 1
   const cplx* gk;         // [D]                     fxft[k]/sqrt(D)
   const cplx* phase;      // [D]                     exp(2 pi i k / D) = exp(i pi q / D), q = 2k
   cplx* rbuf;             // [batch][2][smax][chi*chi]     R_{n,y} row-major (q x b_n), ld chi
@@ -202,6 +207,8 @@ struct DqaDev {
   int* nsv;               // [batch][N]
   cplx* tmk;              // [batch][n_xi][kh]             <psi|Phi_{mu,k}|psi>
   cplx* eps;              // [batch][P+1]
+  cplx* escratch;         // [batch]                       dqa_energy's result (never aliases the trace)
+  double* discw;          // [batch][N]                    relative discarded weight of the last truncation at cut l
   int* bdmon;             // [batch][P*n_xi]
   int* status;            // [batch]  bit0: non-finite, bit1: zero norm, bit2: Jacobi not converged
   unsigned long long* counters;  // [batch][DQA_NCNT] rotations, sweeps, svds, qr columns, flops: LQ, Jacobi, sector QR, theta GEMMs; thread-0 cycles of sector QR phases (GEMM+load, factor, R/Q out) and #CTAs; of LQ phases (panel, T, trailing) and #CTAs

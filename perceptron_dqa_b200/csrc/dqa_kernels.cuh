@@ -389,7 +389,7 @@ __global__ void k_theta0(DqaDev d, int mu, int p) {
     const int j = i % qn, s = i / qn;
     cplx acc = cmk(0.0, 0.0);
     for (int c = 0; c < br; ++c) acc = cfma(r1[j * chi + c], a0[s * chi + c], acc);
-    const cplx u = d.uz[(size_t)p * d.D + yp + (hb ^ s)];
+    const cplx u = d.uz[((size_t)d.tab[inst] * d.P + p) * d.D + yp + (hb ^ s)];
     th[(size_t)s * d.ld_theta + off + j] = cmul(u, acc);
   }
 }
@@ -847,26 +847,50 @@ __device__ __forceinline__ void jacobi_tail(const DqaDev& d, int inst, int l, in
   }
   __syncthreads();
   if (tid == 0) {
-    double tot = 0.0;
-    for (int i = 0; i < k; ++i) tot += ssorted[i] * ssorted[i];
-    const double thr = (1.0 - d.cutoff) * tot;
-    double csp = 0.0, ckeep = 0.0;
-    int cnt = 0;
+    // _trim_and_renorm_svd_result (lib/tenn.py:317-354) with the plan's policy; the reference's call site
+    // (lib/tenn.py:238) fixes cutoff 1e-10, mode 4 (relative cumulative s^2), renorm 2, absorb right
+    const int mode = d.cutoff_mode;
+    const bool pw2 = (mode == 3 || mode == 4 || mode < 3);
+    double tot = 0.0, tot2 = 0.0;
     for (int i = 0; i < k; ++i) {
-      csp += ssorted[i] * ssorted[i];
-      if (csp < thr) cnt++;
+      tot2 += ssorted[i] * ssorted[i];
+      tot += pw2 ? ssorted[i] * ssorted[i] : ssorted[i];
     }
-    int n_chi = cnt + 1;
-    if (n_chi < 1) n_chi = 1;
-    if (n_chi > chi) n_chi = chi;
+    double csp = 0.0, ckeep = 0.0, ckeep2 = 0.0;
+    int cnt = 0, n_chi;
+    if (d.cutoff > 0.0 || d.renorm > 0) {
+      if (mode == 1) {
+        for (int i = 0; i < k; ++i) cnt += ssorted[i] > d.cutoff;
+        n_chi = cnt;
+      } else if (mode == 2) {
+        for (int i = 0; i < k; ++i) cnt += ssorted[i] > d.cutoff * ssorted[0];
+        n_chi = cnt;
+      } else {
+        const double thr = (1.0 - d.cutoff) * tot;
+        for (int i = 0; i < k; ++i) {
+          csp += pw2 ? ssorted[i] * ssorted[i] : ssorted[i];
+          if (mode == 4 || mode == 6) cnt += csp < thr;
+          else cnt += (tot - csp) > d.cutoff;
+        }
+        n_chi = cnt + 1;
+      }
+      if (n_chi < 1) n_chi = 1;
+      if (n_chi > chi) n_chi = chi;
+    } else {
+      n_chi = chi;
+    }
     if (n_chi > k) n_chi = k;
-    for (int i = 0; i < n_chi; ++i) ckeep += ssorted[i] * ssorted[i];
+    for (int i = 0; i < n_chi; ++i) {
+      ckeep += pw2 ? ssorted[i] * ssorted[i] : ssorted[i];
+      ckeep2 += ssorted[i] * ssorted[i];
+    }
     double sc = 1.0;
     int st = 0;
-    if (!(tot == tot) || tot > 1e300) st |= DQA_ST_NONFINITE;
-    if (tot == 0.0) st |= DQA_ST_ZERONORM;
+    if (!(tot2 == tot2) || tot2 > 1e300) st |= DQA_ST_NONFINITE;
+    if (tot2 == 0.0) st |= DQA_ST_ZERONORM;
     if (!converged) st |= DQA_ST_NOCONV;
-    if (n_chi < k && ckeep > 0.0) sc = sqrt(tot / ckeep);
+    if (n_chi < k && ckeep > 0.0 && d.renorm > 0 && mode >= 3) sc = pw2 ? sqrt(tot / ckeep) : tot / ckeep;
+    d.discw[(size_t)inst * d.N + l] = tot2 > 0.0 ? (tot2 - ckeep2) / tot2 : 0.0;
     if (st) atomicOr(&d.status[inst], st);
     sh_i[1] = n_chi;
     d.scale[inst] = sc;
@@ -1101,8 +1125,11 @@ __global__ void __launch_bounds__(512) k_jacobi(DqaDev d, int l, int mu, int p_s
 // column of a pair is left with the phase e^{i phi} (a gauge of the singular vector).
 // shared: exchange buffers 2 x (groups x mr), reused for the final columns | sig | xn/ssorted | order | sh_i
 // ---------------------------------------------------------------------------------
+#ifndef JSYS_MINB8
+#define JSYS_MINB8 2  // CTAs per SM the 8-row-slot systolic Jacobi is compiled for
+#endif
 template <int RS>
-__global__ void __launch_bounds__(RS * 32, RS >= 8 ? 2 : (RS >= 6 ? 3 : (RS >= 4 ? 6 : 8))) k_jacobi_sys(DqaDev d, int l, int mu, int p_step) {
+__global__ void __launch_bounds__(RS * 32, RS >= 8 ? JSYS_MINB8 : (RS >= 6 ? 3 : (RS >= 4 ? 6 : 8))) k_jacobi_sys(DqaDev d, int l, int mu, int p_step) {
   DQA_DYN_SMEM(smraw);
   const int inst = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
   const int chi = d.chi;
@@ -1279,8 +1306,13 @@ __global__ void __launch_bounds__(RS * 32, RS >= 8 ? 2 : (RS >= 6 ? 3 : (RS >= 4
 // (lib/dQA_utils.py:26-30 + lib/tenn.py:67-81 for a bond-1 MPO), all sites in one launch.
 // grid (N, batch)
 // ---------------------------------------------------------------------------------
-__global__ void k_mixer(DqaDev d, double cb, double sb) {
+__global__ void k_mixer(DqaDev d, double cb, double sb, double one_minus_s, int per_inst) {
   const int site = blockIdx.x, inst = blockIdx.y;
+  if (per_inst) {  // instances with their own dt: beta = (1 - s_p) * dt_inst (dQA_mps.py:88-89)
+    const double beta = one_minus_s * d.dtv[inst];
+    cb = cos(beta);
+    sb = sin(beta);
+  }
   const int chi = d.chi;
   const int* bond = d.bond + inst * (d.N + 1);
   const int bl = bond[site], br = bond[site + 1];
@@ -1483,7 +1515,7 @@ __global__ void k_energy_ext_reduce(const cplx* tmk, const cplx* gk, int n_xi, i
 }
 
 // eps = (1/N) sum_mu [ sum_{k<=D/2} g_k T_k + sum_{0<k<D/2} g_{D-k} conj(T_k) ]; one warp per instance
-__global__ void k_energy_reduce(DqaDev d, int slot) {
+__global__ void k_energy_reduce(DqaDev d, cplx* out, size_t stride) {
   const int inst = blockIdx.x, lane = threadIdx.x;
   cplx acc = cmk(0.0, 0.0);
   const int n = d.n_xi * d.kh;
@@ -1494,5 +1526,5 @@ __global__ void k_energy_reduce(DqaDev d, int slot) {
     if (k > 0 && 2 * k != d.D) acc = cfmac(d.gk[d.D - k], t, acc);
   }
   acc = warp_sum(acc);
-  if (lane == 0) d.eps[(size_t)inst * (d.P + 1) + slot] = cscale(acc, 1.0 / d.N);
+  if (lane == 0) out[(size_t)inst * stride] = cscale(acc, 1.0 / d.N);
 }

@@ -7,7 +7,7 @@ from __future__ import annotations
 import numpy as np
 
 from . import tenn
-from .dQA_mps import mydQA
+from .dQA_mps import _device_index, mydQA
 from .dQA_utils import as_patterns
 
 __all__ = ["mydQA_ancilla", "Hz_mu_singleK_with_ancilla"]
@@ -34,7 +34,7 @@ class mydQA_ancilla(mydQA):
         self.n_ancilla = n_ancilla
 
     def compute_loss(self, psi):
-        return tenn.ops().energy(list(psi), as_patterns(self.dataset), self.fxft, self.n_ancilla)
+        return tenn.ops(_device_index(self.device)).energy(list(psi), as_patterns(self.dataset), self.fxft, self.n_ancilla)
 
     def run(self) -> None:
         raise Exception("do not use this class to run dQA!")

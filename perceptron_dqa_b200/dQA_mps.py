@@ -6,7 +6,9 @@
 Same constructor, methods and public attributes (`loss`, `bd_monitor`, `psi`, `Uk_FT`,
 `fxft`, `N`, `N_xi`, `P`, `dt`, `tau`, `max_bond`, `pp`, `dataset`).  Extras that default
 to the reference behaviour: a 3-d `dataset` (batch, N_xi, N) evolves `batch` independent
-realisations at once on this GPU (`.eps` then holds the (batch, P+1) traces).
+realisations at once on this GPU (`.eps` then holds the (batch, P+1) traces); with such a
+batch `dt` may be a sequence of `batch` values (the dt grid of benchmarker-mps.py:50-57 on the
+ensemble dimension: one Fourier table per distinct dt, `Uk_FT` is then (n_dt, N+1, P)).
 Host code here only builds the two small Fourier tables (as dQA_mps.py:62-66 does) and
 moves results; all step arithmetic is CUDA.
 """
@@ -15,7 +17,7 @@ from __future__ import annotations
 import numpy as np
 import numpy.fft as fft
 
-from ._lib import Plan
+from ._lib import DqaNumericError, Plan
 from .dQA_utils import PerceptronHamiltonian, as_patterns
 
 __all__ = ["mydQA"]
@@ -41,8 +43,16 @@ class mydQA:
         self.batch = 1 if self._xi.ndim == 2 else self._xi.shape[0]
         self.N_xi, self.N = self._xi.shape[-2], self._xi.shape[-1]
         self.P = P
-        self.dt = dt
-        self.tau = dt * P
+        if np.ndim(dt) == 0:
+            self.dt, self._dts = dt, None
+            self.tau = dt * P
+        else:  # one dt per realisation of the batch
+            self._dts = np.asarray(dt, dtype=np.float64).reshape(-1)
+            if self._dts.shape[0] != self.batch:
+                raise ValueError("dt must be a scalar or one value per realisation of the batch")
+            self._dt_values, self._dt_index = np.unique(self._dts, return_inverse=True)
+            self.dt = self._dts
+            self.tau = self._dts * P
         self.max_bond = max_bond
         self.pp = 0
         self._plan_kw = dict(_plan_kw or {})
@@ -55,12 +65,25 @@ class mydQA:
     # -- tables (dQA_mps.py:62-66) -------------------------------------------------------
     def init_fourier(self) -> None:
         f = PerceptronHamiltonian.f_perceptron(range(self.N + 1), self.N)
-        self.Uk_FT = np.zeros((self.N + 1, self.P), dtype=np.complex128)
-        for p in range(self.P):
-            self.Uk_FT[:, p] = fft.fft(np.exp(-1.0j * ((p + 1) / self.P) * self.dt * f), norm="ortho")
+
+        def table(dt):
+            uk = np.zeros((self.N + 1, self.P), dtype=np.complex128)
+            for p in range(self.P):
+                uk[:, p] = fft.fft(np.exp(-1.0j * ((p + 1) / self.P) * dt * f), norm="ortho")
+            return uk
+
+        self.Uk_FT = table(self.dt) if self._dts is None else np.stack([table(v) for v in self._dt_values])
         self.fxft = fft.fft(f, norm="ortho")
         if self._plan is not None:
-            self._plan.set_fourier(self.Uk_FT, self.fxft)
+            self._set_tables(self._plan, main=True)
+
+    def _set_tables(self, pl, main):
+        if self._dts is None:
+            pl.set_fourier(self.Uk_FT, self.fxft)
+        elif main:
+            pl.set_fourier_tables(self.Uk_FT, self.fxft, self._dt_index, self._dts)
+        else:  # single-instance helper plans (compute_loss) only need fxft; any table will do
+            pl.set_fourier(self.Uk_FT[0], self.fxft)
 
     # -- plan handling ---------------------------------------------------------------------
     def _make_plan(self, chi, batch, xi):
@@ -68,9 +91,11 @@ class mydQA:
             raise RuntimeError("call init_fourier() first")
         kw = dict(self._plan_kw)
         kw.setdefault("device", _device_index(self.device))
-        pl = Plan(self.N, self.N_xi, self.P, self.dt, chi, batch=batch, **kw)
+        main = batch == self.batch and self._dts is not None
+        dt0 = self.dt if self._dts is None else float(self._dts[0])
+        pl = Plan(self.N, self.N_xi, self.P, dt0, chi, batch=batch, n_tables=len(self._dt_values) if main else 1, **kw)
         pl.set_patterns(xi)
-        pl.set_fourier(self.Uk_FT, self.fxft)
+        self._set_tables(pl, main)
         return pl
 
     @property
@@ -123,11 +148,24 @@ class mydQA:
         """One dQA step; returns eps(s_p) like the reference (dQA_mps.py:84-119)."""
         if self.plan.pp != self.pp:
             self.plan.pp = self.pp
-        self.plan.step(1)
-        self.pp += 1
-        self._psi_cache = None
-        self._pull(self.pp)
+        self._step_and_pull(1)
         return self.loss[-1][1]
+
+    def _step_and_pull(self, n):
+        """n steps, then the traces.  If an instance fails numerically the library has still completed (and
+        recorded) the steps: keep `pp`, `loss` and `bd_monitor` in line with the device before re-raising."""
+        first = self.pp + 1
+        try:
+            self.plan.step(n)
+        except DqaNumericError:
+            self.pp = self.plan.pp
+            self._psi_cache = None
+            if self.pp >= first:
+                self._pull(first)
+            raise
+        self.pp += n
+        self._psi_cache = None
+        self._pull(first)
 
     def run(self, skip_jit=0, print_info: bool = True, chunk: int = 0) -> None:
         """Run all P steps from |+>^N.  `skip_jit` is accepted and ignored (it is a no-op in
@@ -144,11 +182,7 @@ class mydQA:
         self._pull(0)
         chunk = chunk or self.P
         while self.pp < self.P:
-            n = min(chunk, self.P - self.pp)
-            first = self.pp + 1
-            self.plan.step(n)
-            self.pp += n
-            self._pull(first)
+            self._step_and_pull(min(chunk, self.P - self.pp))
 
     def plot_loss(self):
         """dQA_mps.py:177-185."""

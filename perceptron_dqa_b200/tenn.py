@@ -14,20 +14,23 @@ import numpy as np
 
 from ._lib import Ops
 
-_ops = None
+_ops = {}  # one op context (device scratch + handle) per CUDA device
+_forced = None
 
 
-def ops() -> Ops:
-    global _ops
-    if _ops is None:
-        _ops = Ops()
-    return _ops
+def ops(device: int = 0) -> Ops:
+    if _forced is not None:
+        return _forced
+    o = _ops.get(device)
+    if o is None:
+        o = _ops[device] = Ops(device=device)
+    return o
 
 
 def set_ops(o):
     """Use a specific op context (the CPU tests hand in one backed by the SIMT-emulator build)."""
-    global _ops
-    _ops = o
+    global _forced
+    _forced = o
 
 
 # ---- layout helpers (pure reshapes, lib/tenn.py:31-61) --------------------------------------------

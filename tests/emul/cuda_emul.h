@@ -324,6 +324,8 @@ static inline cudaError_t cudaGetLastError() { return 0; }
 static inline cudaError_t cudaPeekAtLastError() { return 0; }
 static inline cudaError_t cudaSetDevice(int) { return 0; }
 static inline cudaError_t cudaGetDevice(int* d) { *d = 0; return 0; }
+enum cudaDeviceAttr { cudaDevAttrMaxSharedMemoryPerBlockOptin = 97 };
+static inline cudaError_t cudaDeviceGetAttribute(int* v, cudaDeviceAttr, int) { *v = 227 * 1024; return 0; }
 static inline const char* cudaGetErrorString(cudaError_t) { return "emul"; }
 template <class F>
 static inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAttribute, int) { return 0; }

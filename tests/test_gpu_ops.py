@@ -103,3 +103,19 @@ def test_statevector_validator(T):
     # (measured: the dynamics is strongly entangling), so only an envelope is asserted there
     assert first[0] > first[1] > first[2], first
     assert max(worst) < 5e-3, worst
+
+
+def test_mydqa_ancilla_vs_reference_fixture():
+    """tests/golden/ancilla_loss.npz holds the answers of the UNMODIFIED lib/dQA_loss.py (mydQA_ancilla.compute_loss,
+    run through the import shim by oracle/make_ancilla_golden.py) on external MPS with 0/1/3 ancilla sites, with and
+    without flip_endian."""
+    from helpers import unpack_mps
+    from perceptron_dqa_b200.dQA_loss import mydQA_ancilla
+
+    g = golden("ancilla_loss")
+    for ci in g["cases"]:
+        psi = unpack_mps(g[f"case{ci}_bonds"], g[f"case{ci}_mps"])
+        obj = mydQA_ancilla(g["xi"], P=int(g["P"]), dt=float(g["dt"]), n_ancilla=int(g[f"case{ci}_n_anc"]),
+                            flip_endian=bool(g[f"case{ci}_flip"]))
+        want = complex(g[f"case{ci}_eps"])
+        assert abs(obj.compute_loss(psi) - want) < 1e-12 * max(1.0, abs(want)), ci

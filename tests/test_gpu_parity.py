@@ -305,3 +305,116 @@ def test_errors_are_reported():
         pl.set_patterns(np.zeros((1, 5, 7), dtype=np.int8))  # not +-1
     with pytest.raises(DqaError):
         Plan(7, 5, 4, 1.0, 65)  # chi beyond what the kernels support
+
+
+def test_plans_of_different_size_interleaved(factory):
+    """A second plan with a smaller bond must not lower the shared-memory opt-in of the kernels under a live plan
+    (the attribute is per kernel, process-wide): chi=32 plan, then a chi=8 plan, then the first one steps again."""
+    g = golden("c3_n21_chi32")
+    big = ps.make(factory, g)
+    big.reset_plus()
+    big.step(1)
+    gs = golden("n7_chi4")
+    small = ps.make(factory, gs)
+    small.reset_plus()
+    small.step(2)
+    big.step(1)  # k_lq at N=21, chi=32 needs > 48 KB of dynamic shared memory
+    small.step(1)
+    assert not big.status().any() and not small.status().any()
+    assert np.abs(small.eps_trace()[0, :4] - gs["eps"][:4]).max() < 1e-10
+    ref = ps.make(factory, g)
+    ref.reset_plus()
+    ref.step(2)
+    assert np.array_equal(ref.eps_trace()[0, :3], big.eps_trace()[0, :3])
+
+
+def test_dt_grid_in_one_batch():
+    """The dt grid of benchmarker-mps.py:50-57 on the ensemble dimension: instances with different dt (their own
+    Fourier tables and mixer angles) in one plan reproduce the single-dt runs."""
+    from perceptron_dqa_b200.dQA_mps import mydQA
+
+    g = golden("n7_chi4")
+    xi, P, chi = g["xi"], int(g["P"]), int(g["chi"])
+    dts = [float(g["dt"]), 0.3, float(g["dt"]), 1.1]
+    obj = mydQA(np.stack([xi] * 4), P=P, dt=dts, max_bond=chi)
+    obj.init_fourier()
+    assert obj.Uk_FT.shape == (3, xi.shape[1] + 1, P)
+    obj.run(print_info=False)
+    assert np.abs(obj.eps[0, :6] - g["eps"][:6]).max() < 1e-10
+    assert np.array_equal(obj.eps[0], obj.eps[2])
+    for i in (1, 3):
+        one = mydQA(xi, P=P, dt=dts[i], max_bond=chi)
+        one.init_fourier()
+        one.run(print_info=False)
+        # same kernels, same state: only cos/sin of the mixer angle come from the device instead of the host
+        assert np.abs(obj.eps[i] - one.eps[0]).max() < 1e-12
+        assert abs(obj.eps[i, -1] - obj.eps[0, -1]) > 1e-6  # and the dt really differs
+
+
+def test_truncation_policy_fields(factory):
+    """cutoff_mode / renorm as plan fields (lib/tenn.py:238 hard-codes 4 / 2): a sub-step under another policy
+    follows the numpy statement of the same algorithm with that policy; absorb != right is refused."""
+    import sector_model as S
+    from helpers import snapshots
+    from perceptron_dqa_b200._lib import DqaError, Plan
+
+    g = golden("c1_n12_chi10")
+    xi, P, dt, chi = g["xi"], int(g["P"]), float(g["dt"]), 6
+    hbit, _, _ = O.hamming_tables(xi)
+    p, mu, pre, _post = snapshots(g)[3]
+    pre = O.compress_svd_normalized(O.right_canonize([t.copy() for t in pre], 1), chi)  # bonds <= 6
+    u = S.uz_diagonal(g["Uk_FT"][:, p], xi.shape[1])
+    nbit = np.stack([hbit[mu], 1 - hbit[mu]], axis=1)
+    for mode, renorm, cutoff in ((4, 0, 1e-10), (2, 0, 1e-2), (3, 2, 1e-6), (6, 1, 1e-3), (1, 0, 5e-2)):
+        pl = Plan(xi.shape[1], xi.shape[0], P, dt, chi, cutoff=cutoff, cutoff_mode=mode, renorm=renorm, absorb=1)
+        pl.set_patterns(xi[None])
+        pl.set_fourier(g["Uk_FT"], g["fxft"])
+        pl.set_mps(pre)
+        pl.apply_pattern(p, mu)
+        got = pl.get_mps()
+        stats = []
+        want = S.apply_pattern_sector([t.copy() for t in pre], u, nbit, chi, cutoff=cutoff, cutoff_mode=mode, renorm=renorm, stats=stats)
+        assert [t.shape for t in got] == [t.shape for t in want], (mode, renorm)
+        n2g, n2w = O.mps_norm2(got), O.mps_norm2(want)
+        assert abs(n2g - n2w) < 1e-12 * max(1.0, n2w)
+        assert abs(abs(O.overlap(got, want)) / np.sqrt(n2g * n2w) - 1.0) < 1e-12
+        # per-bond discarded weight trace
+        w = pl.truncation_error()
+        for l, _shape, sv, n_chi in stats:
+            tot = float((sv**2).sum())
+            assert abs(w[l] - float((sv[n_chi:]**2).sum()) / tot) < 1e-13
+    with pytest.raises(DqaError):
+        Plan(xi.shape[1], xi.shape[0], P, dt, chi, cutoff_mode=4, renorm=2, absorb=0)
+    with pytest.raises(DqaError):
+        Plan(xi.shape[1], xi.shape[0], P, dt, chi, cutoff_mode=7, renorm=2, absorb=1)
+
+
+def test_status_is_cleared_by_a_new_state_and_driver_resyncs():
+    """A numeric failure is sticky only until a state is loaded again; mydQA keeps pp / loss in line with the
+    device when a step raises (the library completes and records the step before reporting the status)."""
+    import torch
+
+    from perceptron_dqa_b200._lib import DqaNumericError
+    from perceptron_dqa_b200.dQA_mps import mydQA
+
+    g = golden("n7_chi4")
+    obj = mydQA(g["xi"], P=int(g["P"]), dt=float(g["dt"]), max_bond=int(g["chi"]))
+    obj.init_fourier()
+    obj.plan.reset_plus()
+    obj._pull(0)
+    good = obj.plan.get_mps(0)
+    bad = [t.copy() for t in good]
+    bad[3][...] = np.nan
+    obj.plan.set_mps(bad)
+    with pytest.raises(DqaNumericError):
+        obj.single_step()
+    assert obj.pp == 1 == obj.plan.pp and len(obj.loss) == 2  # the completed step is on record
+    assert obj.plan.status()[0] != 0
+    obj.plan.set_mps(good)  # a fresh state clears the status word
+    assert obj.plan.status()[0] == 0
+    obj.pp = 0
+    obj.loss, obj.bd_monitor = obj.loss[:1], []
+    e1 = obj.single_step()
+    assert abs(e1 - g["eps"][1]) < 1e-10 and obj.pp == 1
+    obj.plan.clear_status()
+    torch.cuda.synchronize()

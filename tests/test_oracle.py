@@ -148,3 +148,25 @@ def test_live_reference_if_present():
     ua, va = mod.svd_truncated(x, cutoff=1e-10, absorb=1, max_bond=3, cutoff_mode=4, renorm=2)
     ub, vb = O.svd_truncated(x, cutoff=1e-10, absorb=1, max_bond=3, cutoff_mode=4, renorm=2)
     assert np.abs(ua - ub).max() < 1e-14 and np.abs(va - vb).max() < 1e-14
+
+
+def test_ancilla_loss_port_matches_reference_fixture_and_live():
+    """a11: the port's compute_loss(n_ancilla) against answers of the unmodified lib/dQA_loss.py
+    (tests/golden/ancilla_loss.npz) and, where the reference tree exists, against a live call."""
+    import ref_runner
+    from helpers import unpack_mps
+
+    g = golden("ancilla_loss")
+    live = ref_runner.load_ancilla()[1] if ref_runner.available() else None
+    fx = O.fourier_tables(g["xi"].shape[1], int(g["P"]), float(g["dt"]))[1]
+    for ci in g["cases"]:
+        psi = unpack_mps(g[f"case{ci}_bonds"], g[f"case{ci}_mps"])
+        xi = g["xi"][:, ::-1] if bool(g[f"case{ci}_flip"]) else g["xi"]
+        want = complex(g[f"case{ci}_eps"])
+        got = O.compute_loss(psi, xi, fx, n_ancilla=int(g[f"case{ci}_n_anc"]))
+        assert abs(got - want) < 1e-12 * max(1.0, abs(want))
+        if live is not None:
+            with ref_runner.quiet():
+                obj = live.mydQA_ancilla(g["xi"].astype(np.int64), P=int(g["P"]), dt=float(g["dt"]),
+                                         n_ancilla=int(g[f"case{ci}_n_anc"]), flip_endian=bool(g[f"case{ci}_flip"]))
+                assert abs(complex(obj.compute_loss(psi)) - want) < 1e-13 * max(1.0, abs(want))

@@ -45,6 +45,10 @@ def parse():
     ap.add_argument("--batch", type=int, default=888, help="realisations per GPU (888 = 148 SMs x 6: whole waves at 2 and 3 CTAs/SM)")
     ap.add_argument("--cpu-seconds", type=float, default=200.0, help="budget of the CPU legs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ensemble-total", type=int, default=0,
+                    help="C4 mode (BASELINE.json config 4): a FIXED ensemble of this many distinct realisations split over the "
+                         "ranks (strong scaling), full P-step run from |+>, all-reduced eps(s) inside the timed region")
+    ap.add_argument("--save", default="", help="C4 mode: write mean/sem of eps(s) to this .npz")
     ap.add_argument("--no-roofline", action="store_true")
     return ap.parse_args()
 
@@ -52,11 +56,13 @@ def parse():
 def ensemble_patterns(a, rank, batch):
     """C4 law: iid uniform +-1, default_rng(20230317); realisation r of the job is
     row r of that table; global realisation 0 is the reference's patterns_17-21.1.npy."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rows = max(1024, batch * world)  # the first 1024 rows are the C4 table; larger jobs continue the same stream (no repeats)
     rng = np.random.default_rng(20230317)
-    table = (2 * rng.integers(0, 2, size=(1024, 17, 21)) - 1).astype(np.int8)
+    table = (2 * rng.integers(0, 2, size=(rows, 17, 21)) - 1).astype(np.int8)
     if (a.n, a.nxi) != (21, 17):
-        table = (2 * rng.integers(0, 2, size=(1024, a.nxi, a.n)) - 1).astype(np.int8)
-    idx = (rank * batch + np.arange(batch)) % 1024
+        table = (2 * rng.integers(0, 2, size=(rows, a.nxi, a.n)) - 1).astype(np.int8)
+    idx = rank * batch + np.arange(batch)
     xi = table[idx].copy()
     if rank == 0 and (a.n, a.nxi) == (21, 17):
         g = np.load(os.path.join(ROOT, "tests", "golden", "c2_n21_chi10.npz"))
@@ -70,47 +76,67 @@ def workload_name(a, batch, world):
 
 
 # ----------------------------------------------------------------------------------------
-# CPU legs: the oracle (numpy restatement of the reference algorithm) on the host cores
+# CPU legs.  The baseline is the reference's OWN implementation: dQA_mps.py / lib/tenn.py / lib/dQA_utils.py,
+# unmodified, imported through the numpy-backed jax shim (oracle/ref_runner.py) in complex128 -- from /root/reference
+# where it exists, else from the verbatim copies oracle/make_ref.py staged in the git-ignored oracle/_ref/ (they travel
+# to the GPU box).  Only if neither is present does the numpy port (oracle/dqa_oracle.py) stand in (kind "port").
+# One process per host core, one realisation per process, 1 BLAS thread each (OpenBLAS threading slows these sizes).
 # ----------------------------------------------------------------------------------------
-def _random_saturated_mps(n, chi, seed):
-    """A normalised random MPS with the bond profile min(chi, 2^i, 2^(N-i)) -- the shape the
-    state has at p ~ P/2; LAPACK cost does not depend on the values."""
-    rng = np.random.default_rng(seed)
-    bonds = [min(chi, 2 ** i, 2 ** (n - i)) for i in range(n + 1)]
-    mps = [rng.normal(size=(bonds[i], 2, bonds[i + 1])) + 1j * rng.normal(size=(bonds[i], 2, bonds[i + 1])) for i in range(n)]
-    return mps
+def _evolved_state(n, nxi, chi):
+    """A real evolved state with saturated bonds: the reference's own MPS after two steps at N=21, chi=32
+    (tests/golden/c3_n21_chi32.npz, written by the unmodified reference).  None for other sizes."""
+    if (n, nxi, chi) != (21, 17, 32):
+        return None
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from helpers import golden, unpack_mps
+
+    g = golden("c3_n21_chi32")
+    return unpack_mps(g["snap1_post_bonds"], g["snap1_post_flat"])
 
 
 def _cpu_worker(args):
-    """One sample on one core: one pattern sub-step (U_z apply, right-canonise, truncate:
-    dQA_mps.py:94-103) plus the energy of two of the N_xi patterns (dQA_mps.py:68-81)."""
-    (n, nxi, chi, P, dt, seed, mps) = args
+    """Whole dQA steps of one realisation on one core.  Returns (kind, [seconds per step], untimed warm-up steps)."""
+    (n, nxi, chi, P, dt, xi, nsteps, want) = args
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import dqa_oracle as O
+    import ref_runner
 
-    rng = np.random.default_rng(seed)
-    xi = (2 * rng.integers(0, 2, size=(nxi, n)) - 1).astype(np.int8)
+    state = _evolved_state(n, nxi, chi)
+    warm = 0 if state is not None else 1
+    times = []
+    if want == "reference" and ref_runner.available():
+        mod = ref_runner.load(sgn0fix=False)  # verbatim, stock code path
+        obj = mod.mydQA(np.asarray(xi).astype(np.float64), P=P, dt=dt, max_bond=chi)
+        obj.init_fourier()
+        obj.psi = state if state is not None else [np.array([[[2 ** -0.5], [2 ** -0.5]]], dtype=np.complex128)] * n
+        obj.pp = P // 2
+        obj.loss, obj.bd_monitor = [], []  # the two traces run() would have created (dQA_mps.py:141-147)
+        with ref_runner.quiet():
+            for k in range(warm + nsteps):
+                t0 = time.perf_counter()
+                obj.single_step()  # dQA_mps.py:84-119
+                if k >= warm:
+                    times.append(time.perf_counter() - t0)
+        return "reference", times, warm
     o = O.OracleDQA(xi, P, dt, chi)
     o.init_fourier()
+    o.psi = state if state is not None else O.plus_state(n)
     o.pp = P // 2
-    if mps is None:
-        mps = _random_saturated_mps(n, chi, seed)
-        mps = O.right_canonize(mps, 1)
-        mps = O.compress_svd_normalized(mps, chi)
-    t0 = time.perf_counter()
-    psi = o.apply_pattern([t.copy() for t in mps], 0)
-    t1 = time.perf_counter()
-    O.compute_loss(psi, xi[:2], o.fxft)
-    t2 = time.perf_counter()
-    return (t1 - t0, (t2 - t1) / 2.0)
+    o.loss, o.bd_monitor = [], []
+    for k in range(warm + nsteps):
+        t0 = time.perf_counter()
+        o.single_step()
+        if k >= warm:
+            times.append(time.perf_counter() - t0)
+    return "port", times, warm
 
 
-def cpu_sample(a, cores, state=None):
-    """Run one sample on each of `cores` processes at once; returns the estimated seconds one
-    full dQA step takes on one core = N_xi * (t_substep + t_energy_per_pattern)."""
+def cpu_steps(a, cores, nsteps, want="reference"):
+    """`nsteps` whole steps on each of `cores` processes at once.  Returns (kind, mean s per step per core, wall, warm)."""
     import multiprocessing as mp
 
-    jobs = [(a.n, a.nxi, a.chi, a.P, a.dt, 1000 + i, state) for i in range(cores)]
+    xi = ensemble_patterns(a, 0, max(cores, 1))
+    jobs = [(a.n, a.nxi, a.chi, a.P, a.dt, xi[i], nsteps, want) for i in range(cores)]
     t0 = time.perf_counter()
     if cores == 1:
         res = [_cpu_worker(jobs[0])]
@@ -118,8 +144,31 @@ def cpu_sample(a, cores, state=None):
         with mp.get_context("spawn").Pool(cores) as pool:
             res = pool.map(_cpu_worker, jobs)
     wall = time.perf_counter() - t0
-    per_step = [a.nxi * (ts + te) for ts, te in res]
-    return float(np.mean(per_step)), wall
+    per_step = [t for _k, ts, _w in res for t in ts]
+    return res[0][0], float(np.mean(per_step)), wall, res[0][2]
+
+
+def cpu_same_algorithm(a):
+    """One step of the SECTOR algorithm (what the kernels run) in numpy on one core (oracle/sector_model.py): splits the
+    GPU-vs-reference ratio into an algorithmic and a hardware factor.  None if no evolved state is at hand."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import dqa_oracle as O
+    import sector_model as S
+
+    psi = _evolved_state(a.n, a.nxi, a.chi)
+    if psi is None:
+        return None
+    xi = ensemble_patterns(a, 0, 1)[0]
+    hbit, _, _ = O.hamming_tables(xi)
+    uk, fx = O.fourier_tables(a.n, a.P, a.dt)
+    p = a.P // 2
+    u = S.uz_diagonal(uk[:, p], a.n)
+    t0 = time.perf_counter()
+    for mu in range(a.nxi):
+        psi = S.apply_pattern_sector(psi, u, np.stack([hbit[mu], 1 - hbit[mu]], axis=1), a.chi)
+    psi = S.mixer(psi, (1 - (p + 1) / a.P) * a.dt)
+    O.compute_loss_fast(psi, xi, fx)
+    return time.perf_counter() - t0
 
 
 def host_cores():
@@ -129,30 +178,43 @@ def host_cores():
         return os.cpu_count() or 1
 
 
+def cpu_baseline_block(a, nsteps):
+    cores = min(host_cores(), 64)
+    kind, t_step, wall, warm = cpu_steps(a, cores, nsteps)
+    what = ("mydQA.single_step() of the unmodified reference (dQA_mps.py:84-119 through the numpy jax shim, complex128)"
+            if kind == "reference" else "single_step() of the numpy port oracle/dqa_oracle.py (reference files not staged on this box)")
+    start = ("the reference's own evolved MPS (after 2 steps, bonds saturated at chi)" if warm == 0
+             else f"|+>^N and {warm} untimed step")
+    blk = {"value": cores / t_step, "unit": UNIT, "cores": cores, "kind": kind,
+           "sample": f"{nsteps} whole dQA step(s) per core at p=P/2: {what}; start state {start}; {cores} processes x 1 BLAS "
+                     f"thread, one realisation each; {wall:.0f} s wall",
+           "s_per_step_per_core": t_step, "whole_steps": nsteps}
+    t_alg = cpu_same_algorithm(a)
+    if t_alg:
+        blk["same_algorithm"] = {"s_per_step_per_core": t_alg, "value": cores / t_alg, "cores_assumed": cores,
+                                 "what": "one step of oracle/sector_model.py (numpy statement of the sector algorithm the kernels "
+                                         "execute) on one core: reference/this = algorithmic factor, this/GPU = hardware factor"}
+    return blk
+
+
 def run_reference(a):
-    """--impl reference: the reference's algorithm (oracle port; the reference's own Python files
-    cannot travel to the GPU box) on all host cores, one realisation per core."""
+    """--impl reference: whole steps of the reference's own single_step() on all host cores, one realisation per core.
+    A step of the reference at N=21, chi=32 takes ~1.5-2 min per core, so the run is bounded to the number of whole steps
+    that fits --cpu-seconds (at least 2 when --steps >= 2); rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = min(host_cores(), 64)
-    # calibrate with one warm-up sample, then size K so the run stays inside the budget
-    t_step, wall = cpu_sample(a, cores)
-    k = max(1, min(a.steps, int(max(1.0, (a.cpu_seconds - wall)) / max(wall, 1e-3))))
-    steps = []
-    for _ in range(k):
-        t_step, wall = cpu_sample(a, cores)
-        steps.append(t_step)
-    t_step = float(np.mean(steps))
-    value = cores / t_step
-    sample = (f"{k} x (1 of {a.nxi} pattern sub-steps + energy of 2 of {a.nxi} patterns) per core on a random "
-              f"saturated MPS, scaled by {a.nxi}; {cores} processes, 1 BLAS thread each")
+    k = max(1, min(a.steps, 2 if a.cpu_seconds < 400 else int(a.cpu_seconds // 100)))
+    blk = cpu_baseline_block(a, k)
+    value, cores = blk["value"], blk["cores"]
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": k,
-        "warmup": 1, "ms_per_step": 1e3 * t_step / cores, "higher_is_better": True, "scaling": "weak",
+        "warmup": 0, "ms_per_step": 1e3 * blk["s_per_step_per_core"] / cores, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "complex128", "data": "synthetic",
-        "config": {"workload": workload_name(a, a.batch, a.gpus), "note": "CPU arm: one realisation per host core"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "config": {"workload": workload_name(a, a.batch, a.gpus),
+                   "note": f"CPU arm: {cores} host cores, one realisation per core, {k} whole steps each, no extrapolation "
+                           "(numpy has no JIT or cache to warm; start state: see cpu_baseline.sample)"},
+        "cpu_baseline": blk,
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -267,12 +329,17 @@ def run_ours(a):
     k_e2e = max(1, min(a.steps, 3))
     t0 = time.perf_counter()
     e0.record()
+    mom_host = torch.empty(3 * (a.P + 1), dtype=torch.float64).pin_memory()
     for _ in range(k_e2e):
         pl.set_patterns(xi)                      # H2D: the step's patterns
         pl.upload_state(host.data_ptr())         # H2D: the step's input state (pinned)
         pl.step(1)
         pl.download_state(host.data_ptr())       # D2H: the new state
         eps_host[:] = pl.eps_trace()             # D2H: eps(s) trace
+        pl.ensemble_moments_into(mom.data_ptr())  # the path's one collective: sum eps, sum eps^2, #healthy over the job
+        if dist is not None:
+            dist.all_reduce(mom)
+        mom_host.copy_(mom, non_blocking=False)  # D2H: the ensemble result of this step
     e1.record()
     barrier()
     t_e2e = time.perf_counter() - t0
@@ -282,7 +349,7 @@ def run_ours(a):
         dist.all_reduce(t2, op=dist.ReduceOp.MAX)
     e2e_value = B * world * k_e2e / float(t2.item())
     h2d = nbytes + xi.nbytes
-    d2h = nbytes + eps_host.nbytes + 4 * B
+    d2h = nbytes + eps_host.nbytes + 4 * B + mom_host.numel() * 8
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": W,
@@ -295,7 +362,8 @@ def run_ours(a):
                 "steps": k_e2e},
         "gpu_launches": int(launches), "clocks": clocks,
         "single_realisation": None,
-        "ensemble": {"eps_mean_at_last_step": eps_mean, "healthy": n_ok, "allreduce": "nccl" if dist is not None else "none"},
+        "ensemble": {"eps_mean_at_last_step": eps_mean, "healthy": n_ok, "distinct_realisations": B * world,
+                     "allreduce": ("nccl, inside the e2e region every step" if dist is not None else "none (1 rank); moments inside the e2e region")},
         "status_nonzero": int(np.count_nonzero(pl.status())),
     }
 
@@ -307,7 +375,9 @@ def run_ours(a):
         pl.step(1)
         fam_ms, fam_n = pl.profile_end()
         cnt = pl.counters().sum(0).astype(np.float64)
-        peak = pl.fp64_peak_tflops()
+        peaks64 = fp64_peaks(pl, local)
+        peak_name = max(peaks64, key=peaks64.get)
+        peak = peaks64[peak_name]
         bonds = pl.bonds(0)
         e_fl = sum(16.0 * (bonds[i] ** 2 * bonds[i + 1] + bonds[i] * bonds[i + 1] ** 2) for i in range(a.n))
         flops = {"jacobi": cnt[5], "lq": cnt[4], "sector_qr": cnt[6], "theta": cnt[7],
@@ -323,8 +393,10 @@ def run_ours(a):
             "kernel": {"jacobi": "k_jacobi", "lq": "k_lq", "sector_qr": "k_sector_qr", "theta": "k_theta", "energy": "k_energy"}[dom],
             "bound": "fp64", "achieved": fams[dom]["achieved_tflops"], "peak": peak, "unit": "TFLOP/s",
             "frac": fams[dom]["frac"], "traffic": None,
-            "peak_source": "measured on this GPU by libdqa's DFMA probe (MEASURED_PEAKS.json has no FP64 entry; "
-                           "B200 FP64 vector = FP64 tensor peak)",
+            "peak_source": f"largest of three FP64 peaks measured on this GPU in this run: {peak_name} (MEASURED_PEAKS.json has no "
+                           "FP64 entry): cuBLAS DGEMM 8192^3 via torch.matmul (best of 10, CUDA events), libdqa's register-resident "
+                           "DFMA loop, libdqa's mma.sync m8n8k4 f64 loop",
+            "fp64_peaks_tflops": peaks64,
             "flops_per_launch": fams[dom]["flops_per_step"] / max(1, fams[dom]["launches"]),
             "ms_per_launch": fams[dom]["ms_per_step"] / max(1, fams[dom]["launches"]),
             "share_of_step": fams[dom]["share_of_step"], "families": fams,
@@ -340,14 +412,16 @@ def run_ours(a):
         # capture of the same kernel (one mid-chain launch at this batch), when that summary is present
         try:
             tr = 0.0
-            with open(os.path.join(ROOT, "profiles", f"r01_{line['roofline']['kernel']}_ncu_summary.csv")) as f:
+            prof = next(pth for pth in (os.path.join(ROOT, "profiles", f"{r}_{line['roofline']['kernel']}_ncu_summary.csv") for r in ("r02", "r01"))
+                        if os.path.isfile(pth))
+            with open(prof) as f:
                 for ln in f:
                     parts = ln.strip().split(",")
                     if len(parts) == 3 and parts[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
                         tr += float(parts[2]) * {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[parts[1]]
             if tr > 0:
                 line["roofline"]["traffic"] = tr
-                line["roofline"]["traffic_source"] = (f"profiles/r01_{line['roofline']['kernel']}_ncu_summary.csv: dram read+write of one "
+                line["roofline"]["traffic_source"] = (f"profiles/{os.path.basename(prof)}: dram read+write of one "
                                                       "launch under ncu --set full (batch 888); the kernel is FP64-bound, not HBM-bound")
         except Exception:
             pass
@@ -379,20 +453,148 @@ def run_ours(a):
         torch.cuda.synchronize()
         line["single_realisation"] = {"steps_per_s": 2.0 / (x.elapsed_time(y) * 1e-3), "ms_per_step": x.elapsed_time(y) / 2.0}
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
-        cores = min(host_cores(), 64)
-        state = None
-        t_step, wall = cpu_sample(a, cores, state)
-        line["cpu_baseline"] = {
-            "value": cores / t_step, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"1 of {a.nxi} pattern sub-steps + energy of 2 of {a.nxi} patterns per core on a random saturated MPS, "
-                      f"scaled by {a.nxi}; {cores} processes x 1 BLAS thread; {wall:.0f} s wall",
-            "s_per_step_per_core": t_step}
+        line["cpu_baseline"] = cpu_baseline_block(a, 1)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
     if rank == 0:
         print(json.dumps(line), flush=True)
 
+
+
+def run_c4(a):
+    """BASELINE.json config 4 as stated: a FIXED ensemble of --ensemble-total distinct synthetic realisations (C4 law) split
+    over the ranks, the whole P-step run from |+>^N, and the ensemble mean / standard error of eps(s) all-reduced over
+    NCCL -- everything inside the timed region.  Strong scaling: total work is fixed as ranks are added."""
+    import torch
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the dQA hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    from perceptron_dqa_b200.dQA_mps import mydQA
+    from perceptron_dqa_b200.ensemble import finalize_moments
+
+    total = a.ensemble_total
+    if total % world:
+        raise SystemExit("--ensemble-total must be a multiple of the number of ranks")
+    B = total // world
+    xi = ensemble_patterns(a, rank, B)  # rows rank*B .. rank*B+B-1 of the C4 table: all distinct
+    dev = f"cuda:{local}"
+    obj = mydQA(xi if B > 1 else xi[0], P=a.P, dt=a.dt, max_bond=a.chi, device=local)
+    obj.init_fourier()
+    pl = obj.plan
+    mom = torch.zeros(3 * (a.P + 1), dtype=torch.float64, device=dev)
+    res_host = torch.empty(3 * (a.P + 1), dtype=torch.float64).pin_memory()
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def whole_run():
+        pl.reset_plus()
+        pl.step(a.P)
+        pl.ensemble_moments_into(mom.data_ptr())
+        if dist is not None:
+            dist.all_reduce(mom)
+
+    W = max(3, a.warmup)
+    pl.reset_plus()
+    pl.step(min(W, a.P))
+    if dist is not None:
+        dist.all_reduce(mom)  # NCCL communicator set-up outside the timed region
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    # ---- device-timed: the whole ensemble run + the collective -----------------------------------------------
+    flush.fill_(1)
+    l0 = pl.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    whole_run()
+    e1.record()
+    barrier()
+    launches = pl.launch_count() - l0
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    clocks = sampler.summary()
+    # ---- end to end: host patterns and tables in, ensemble curve out ----------------------------------------------
+    flush.fill_(2)
+    barrier()
+    t0 = time.perf_counter()
+    pl.set_patterns(xi)
+    pl.set_fourier(obj.Uk_FT, obj.fxft)
+    whole_run()
+    res_host.copy_(mom)
+    mean, sem, n_ok = finalize_moments(res_host.numpy())
+    torch.cuda.synchronize()
+    t2 = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+    s_e2e = float(t2.item())
+    status = int(np.count_nonzero(pl.status()))
+    if rank == 0:
+        line = {
+            "metric": METRIC.replace("chi=32", f"chi={a.chi}") + " (C4 ensemble run)", "value": total * a.P / (ms * 1e-3), "unit": UNIT,
+            "n_gpus": world, "steps": a.P, "warmup": W, "ms_per_step": ms / a.P, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "complex128", "data": "synthetic",
+            "config": {"workload": f"C4: fixed ensemble of {total} distinct realisations (default_rng(20230317), iid +-1), N={a.n}, "
+                                   f"N_xi={a.nxi}, chi={a.chi}, P={a.P}, dt={a.dt}, full run from |+>^N, {B} realisations per GPU; timed "
+                                   "region = reset + P steps + ensemble moments + NCCL all-reduce of 3(P+1) doubles",
+                       "l2": f"flushed before the run; working set {pl.workspace_bytes / 2**20:.0f} MiB/GPU", "parallelism": f"ensemble x{world}"},
+            "e2e": {"value": total * a.P / s_e2e, "unit": UNIT, "h2d_bytes_per_step": int((xi.nbytes + obj.Uk_FT.nbytes + obj.fxft.nbytes) / a.P),
+                    "d2h_bytes_per_step": int(res_host.numel() * 8 / a.P), "seconds": s_e2e,
+                    "what": "host patterns + Fourier tables in, whole run, all-reduce, mean/sem of eps(s) out (wall clock, max over ranks)"},
+            "gpu_launches": int(launches), "clocks": clocks, "run_seconds": ms * 1e-3,
+            "ensemble": {"healthy_at_end": float(n_ok[-1]), "eps_mean_first": float(mean[0]), "eps_mean_last": float(mean[-1]),
+                         "eps_sem_last": float(sem[-1]), "status_nonzero_rank0": status,
+                         "allreduce": "nccl (inside the timed region)" if dist is not None else "none (1 rank)"},
+        }
+        if a.save:
+            np.savez_compressed(a.save, s=np.arange(a.P + 1) / a.P, eps_mean=mean, eps_sem=sem, healthy=n_ok, total=total, P=a.P,
+                                dt=a.dt, chi=a.chi, n_gpus=world)
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def fp64_peaks(pl, local):
+    """FP64 roofline denominators measured live: a library DGEMM (independent of this repo's code) and libdqa's two probes."""
+    import torch
+
+    out = {"dfma_probe": pl.fp64_peak_tflops(), "dmma_probe": pl.dmma_peak_tflops()}
+    try:
+        n = 8192
+        x = torch.randn(n, n, dtype=torch.float64, device=f"cuda:{local}")
+        y = torch.randn(n, n, dtype=torch.float64, device=f"cuda:{local}")
+        torch.matmul(x, y)
+        best = 0.0
+        for _ in range(10):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            torch.matmul(x, y)
+            e1.record()
+            torch.cuda.synchronize()
+            best = max(best, 2.0 * n ** 3 / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+        out["cublas_dgemm_8192"] = best
+        del x, y
+    except Exception as exc:  # pragma: no cover
+        out["cublas_dgemm_8192"] = 0.0
+        out["cublas_error"] = str(exc)[:100]
+    return {k: v for k, v in out.items() if isinstance(v, float)}
 
 
 def reference_flops(N, n_xi, chi):
@@ -430,6 +632,8 @@ def main():
     a = parse()
     if a.impl == "reference":
         run_reference(a)
+    elif a.ensemble_total:
+        run_c4(a)
     else:
         run_ours(a)
 

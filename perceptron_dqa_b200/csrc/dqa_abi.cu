@@ -44,6 +44,10 @@ struct dqa_handle {
   bool have_patterns, have_fourier, have_state;
   int t_qr, t_theta, t_svd, t_energy, t_energy_env = 0;  // block sizes
   int t_lq;
+  cudaStream_t cap_stream = nullptr;   // capture stream of the step graph (the handle's own stream may be the legacy one)
+  cudaGraphExec_t step_graph = nullptr;  // one dQA step with the step counter read from the device
+  bool use_graph = false, capturing = false;
+  long long graph_nodes = 0;
   bool jac_sys;
   char err[512];
   // profiling
@@ -111,6 +115,8 @@ static void carve(const dqa_config& c, DqaDev& d, Aux& aux, char* base, size_t* 
   d.uz = cv.take<cplx>((size_t)d.ntab * P * D);
   d.tab = cv.take<int>(B);
   d.dtv = cv.take<double>(B);
+  d.pdev = cv.take<int>(1);
+  d.mixtab = cv.take<double>(2 * P);
   d.gk = cv.take<cplx>(D);
   d.phase = cv.take<cplx>(D);
   d.rbuf = cv.take<cplx>(B * 2 * d.smax * chi * chi);
@@ -245,6 +251,13 @@ extern "C" int dqa_create(dqa_t** out, const dqa_config* cfg) {
   if (h->t_energy_env) h->t_energy = h->t_energy_env;
 #endif
   {
+    const char* env = getenv("DQA_GRAPH");  // 0: plain launches for dqa_step (default: one captured graph per step)
+    h->use_graph = !(env && atoi(env) == 0);
+#ifdef DQA_EMUL
+    h->use_graph = false;
+#endif
+  }
+  {
     const char* env = getenv("DQA_JAC_SYS");  // 0: use the shared-memory-resident Jacobi for every chi
     h->jac_sys = !(env && atoi(env) == 0);
   }
@@ -275,6 +288,10 @@ extern "C" void dqa_destroy(dqa_t* h) {
     cudaEventDestroy(e.a);
     cudaEventDestroy(e.b);
   }
+#ifndef DQA_EMUL
+  if (h->step_graph) cudaGraphExecDestroy(h->step_graph);
+  if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
+#endif
   delete h;
 }
 
@@ -378,6 +395,13 @@ static int set_fourier_impl(dqa_t* h, int ntab, const double* uk_ft, const doubl
     gk[k] = fx[k] / std::sqrt((double)D);
   }
   for (int t = 0; t < ntab; ++t) uz_from_ukft(uk + (size_t)t * D * P, D, P, uz.data() + (size_t)t * P * D);
+  std::vector<double> mix((size_t)2 * P);
+  for (int p = 0; p < P; ++p) {
+    const double beta = (1.0 - (double)(p + 1) / P) * h->cfg.dt;  // dQA_mps.py:88-89
+    mix[2 * p] = std::cos(beta);
+    mix[2 * p + 1] = std::sin(beta);
+  }
+  CK(cudaMemcpyAsync(const_cast<double*>(h->dev.mixtab), mix.data(), sizeof(double) * mix.size(), cudaMemcpyHostToDevice, h->stream));
   std::vector<int> tb(B, 0);
   std::vector<double> dv(B, h->cfg.dt);
   for (int b = 0; b < B; ++b) {
@@ -508,14 +532,15 @@ static int launch_truncate(dqa_t* h, int p, int mu) {
   return DQA_OK;
 }
 
-// slot >= 0: eps trace slot; slot < 0: the scratch vector read by dqa_energy
+// slot >= 0: eps trace slot; -1: the scratch vector read by dqa_energy; -2: trace slot p+1 with p read on the device
 static int launch_energy(dqa_t* h, int slot) {
   const DqaDev& d = h->dev;
   prof_a(h, 4);
   if (d.chi > 16) HL(KE_2, dim3(d.kh, d.n_xi, d.batch), dim3(h->t_energy), energy_smem(d.chi), h->stream, d);
   else HL(KE_1, dim3(d.kh, d.n_xi, d.batch), dim3(h->t_energy), energy_smem(d.chi), h->stream, d);
   if (slot >= 0) HL(k_energy_reduce, dim3(d.batch), dim3(32), 0, h->stream, d, d.eps + slot, (size_t)(d.P + 1));
-  else HL(k_energy_reduce, dim3(d.batch), dim3(32), 0, h->stream, d, d.escratch, (size_t)1);
+  else if (slot == -1) HL(k_energy_reduce, dim3(d.batch), dim3(32), 0, h->stream, d, d.escratch, (size_t)1);
+  else HL(k_energy_reduce, dim3(d.batch), dim3(32), 0, h->stream, d, (cplx*)nullptr, (size_t)(d.P + 1));  // slot from the device step counter
   prof_b(h);
   CK(cudaGetLastError());
   return DQA_OK;
@@ -565,10 +590,10 @@ extern "C" int dqa_apply_pattern(dqa_t* h, int p, int mu) {
   return launch_truncate(h, p, mu);
 }
 
-static int launch_mixer(dqa_t* h, double beta, double one_minus_s, bool per_inst) {
+static int launch_mixer(dqa_t* h, double beta, double one_minus_s, int mode) {
   const DqaDev& d = h->dev;
   prof_a(h, 3);
-  HL(k_mixer, dim3(d.N, d.batch), dim3(128), 0, h->stream, d, std::cos(beta), std::sin(beta), one_minus_s, per_inst ? 1 : 0);
+  HL(k_mixer, dim3(d.N, d.batch), dim3(128), 0, h->stream, d, std::cos(beta), std::sin(beta), one_minus_s, mode);
   prof_b(h);
   CK(cudaGetLastError());
   return DQA_OK;
@@ -576,7 +601,7 @@ static int launch_mixer(dqa_t* h, double beta, double one_minus_s, bool per_inst
 
 extern "C" int dqa_apply_ux(dqa_t* h, double beta) {
   NEED_READY();
-  return launch_mixer(h, beta, 0.0, false);
+  return launch_mixer(h, beta, 0.0, 0);
 }
 
 static int check_status(dqa_t* h) {
@@ -592,9 +617,58 @@ static int step_impl(dqa_t* h, int nsteps, bool check);
 extern "C" int dqa_step(dqa_t* h, int nsteps) { return step_impl(h, nsteps, true); }
 // same launches, no host synchronisation and no status check: lets several handles on different streams overlap
 extern "C" int dqa_step_async(dqa_t* h, int nsteps) { return step_impl(h, nsteps, false); }
+// One dQA step captured as a CUDA graph: the launch grid depends only on (N, n_xi, chi, batch), never on data, and every
+// kernel that needs the step index reads it from device memory (p < 0), so the same executable graph replays for every
+// step.  Pays off when the kernels are short (a single realisation, small bonds): 1 431 launches per step at N=21.
+static int build_step_graph(dqa_t* h) {
+  if (!h->cap_stream) CK(cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking));
+  cudaStream_t user = h->stream;
+  const long long l0 = h->launches;
+  h->stream = h->cap_stream;
+  h->capturing = true;
+  cudaError_t e = cudaStreamBeginCapture(h->cap_stream, cudaStreamCaptureModeThreadLocal);
+  int rc = DQA_OK;
+  if (e == cudaSuccess) {
+    for (int mu = 0; mu < h->cfg.n_xi && rc == DQA_OK; ++mu) {
+      rc = launch_canonize(h, mu);
+      if (rc == DQA_OK) rc = launch_truncate(h, -1, mu);
+    }
+    if (rc == DQA_OK) rc = launch_mixer(h, 0.0, 0.0, 2);
+    if (rc == DQA_OK) rc = launch_energy(h, -2);
+    if (rc == DQA_OK) HL(k_advance, dim3(1), dim3(32), 0, h->stream, h->dev);
+    cudaGraph_t g = nullptr;
+    e = cudaStreamEndCapture(h->cap_stream, &g);
+    if (e == cudaSuccess && rc == DQA_OK) e = cudaGraphInstantiate(&h->step_graph, g, 0);
+    if (g) cudaGraphDestroy(g);
+  }
+  h->stream = user;
+  h->capturing = false;
+  h->graph_nodes = h->launches - l0;
+  h->launches = l0;
+  if (e != cudaSuccess || rc != DQA_OK) {
+    cudaGetLastError();
+    h->step_graph = nullptr;
+    h->use_graph = false;  // fall back to plain launches, which report their own errors
+  }
+  return DQA_OK;
+}
+
 static int step_impl(dqa_t* h, int nsteps, bool check) {
   NEED_READY();
   if (nsteps < 0 || h->pp + nsteps > h->cfg.P) return fail(h, DQA_EINVAL, "step %d + %d exceeds P=%d", h->pp, nsteps, h->cfg.P);
+  if (h->use_graph && !h->profiling && nsteps > 0) {
+    if (!h->step_graph) build_step_graph(h);
+    if (h->step_graph) {
+      const int p0 = h->pp;
+      CK(cudaMemcpyAsync(h->dev.pdev, &p0, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+      for (int it = 0; it < nsteps; ++it) {
+        CK(cudaGraphLaunch(h->step_graph, h->stream));
+        h->launches += h->graph_nodes;
+        h->pp++;
+      }
+      return check ? check_status(h) : DQA_OK;
+    }
+  }
   for (int it = 0; it < nsteps; ++it) {
     const int p = h->pp;
     const double s_p = (double)(p + 1) / h->cfg.P;
@@ -605,7 +679,7 @@ static int step_impl(dqa_t* h, int nsteps, bool check) {
       rc = launch_truncate(h, p, mu);
       if (rc) return rc;
     }
-    int rc = launch_mixer(h, beta, 1.0 - s_p, h->dev.ntab > 1);  // several tables: beta = (1 - s_p) * dt of each instance
+    int rc = launch_mixer(h, beta, 1.0 - s_p, h->dev.ntab > 1 ? 1 : 0);  // several tables: beta = (1 - s_p) * dt of each instance
     if (rc) return rc;
     rc = launch_energy(h, p + 1);
     if (rc) return rc;

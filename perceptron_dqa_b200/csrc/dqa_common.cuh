@@ -194,6 +194,9 @@ struct DqaDev {
   const cplx* uz;         // [ntab][P][D]            u_p(x) = exp(-i gamma_p f(x)), one table per distinct dt
   const int* tab;         // [batch]                 Fourier table of each instance
   const double* dtv;      // [batch]                 dt of each instance (mixer angle), only read when ntab > 1
+  int* pdev;              // [1]                     the step counter p on the device: kernels launched with p < 0 read it, so a
+                          //                         captured CUDA graph of one step replays for every step
+  const double* mixtab;   // [P][2]                  cos, sin of the mixer angle (1 - s_p) dt, host-computed (single-dt plans)
   const cplx* gk;         // [D]                     fxft[k]/sqrt(D)
   const cplx* phase;      // [D]                     exp(2 pi i k / D) = exp(i pi q / D), q = 2k
   cplx* rbuf;             // [batch][2][smax][chi*chi]     R_{n,y} row-major (q x b_n), ld chi

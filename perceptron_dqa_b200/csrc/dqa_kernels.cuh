@@ -227,6 +227,11 @@ __device__ __forceinline__ void sqr_apply(cplx (&col)[MAXS], const cplx* vk, cpl
   }
 }
 
+// Measured and rejected (round 2): reflectors in UNSCALED form (u = [alpha - beta; x], H^H = I - t u u^H, t = -1/(beta d)) with
+// every consumer group deriving (beta, d, t) for itself from the published (alpha, |x|^2), so that neither the square root nor
+// the reciprocal nor a scaling pass sits on the owner's path between two block barriers: 3-10 % SLOWER than the scaled form
+// above at every bond dimension (chi=32: 310 vs 300 ms per step; 40.3k vs 37.9k cycles in the factor loop).  At three CTAs per
+// SM the ~45 extra FP64-path instructions per warp and reflector cost more than the shorter hand-off saves.
 template <int MAXS>
 __global__ void __launch_bounds__(MAXS <= 8 ? 256 : (MAXS == 10 ? 320 : (MAXS == 12 ? 384 : 512)), MAXS <= 4 ? 4 : (MAXS <= 8 ? SQR_MINB : (MAXS <= SQR_TWO_UPTO ? 2 : 1))) k_sector_qr(DqaDev d, int n, int mu) {
   DQA_DYN_SMEM(smraw);
@@ -374,8 +379,9 @@ __device__ __forceinline__ int qdim_prefix(const int* qd, int y) {
 // k_theta0: Theta_0[(s), (j,y')] = u_p(y' + nbit_0(s)) * sum_c R_{1,y'}[j,c] A_0[0,s,c]
 // grid (N sectors of bond 1, batch)
 // ---------------------------------------------------------------------------------
-__global__ void k_theta0(DqaDev d, int mu, int p) {
+__global__ void k_theta0(DqaDev d, int mu, int p_arg) {
   const int yp = blockIdx.x, inst = blockIdx.y, tid = threadIdx.x, nt = blockDim.x;
+  const int p = p_arg >= 0 ? p_arg : *d.pdev;
   const int chi = d.chi;
   const int* qd = d.qdim + ((size_t)inst * (d.N + 1) + 1) * d.smax;
   const int qn = qd[yp], off = qdim_prefix(qd, yp);
@@ -774,6 +780,12 @@ __global__ void __launch_bounds__(1024) k_lq(DqaDev d, int l) {
   }
 }
 
+// Measured and rejected (round 2): the panel of k_lq held in REGISTERS, one column per thread (544 threads), with one
+// block-wide reduction per reflector (a 16-slot shuffle butterfly per warp for |x|^2 and the dots with all later panel
+// rows, one shared-memory hand-off, one barrier) and every thread deriving the reflector scalars for itself.  It removes
+// the 975 KB of shared-memory traffic per panel, and was SLOWER: 219 vs 178 ms per step at batch 888, chi=32 (panel phase
+// 177k vs 146k cycles per CTA; alone on the GPU 124k vs 110k): the block-wide reduction of 15 values costs ~1 900 cycles
+// per reflector, more than the four passes over the panel it replaces.
 // ---------------------------------------------------------------------------------
 // k_jacobi (bonds above 32; k_jacobi_sys below handles chi <= 32): SVD of L (mr x k) by one-sided Jacobi + the reference's trim rule
 // (lib/tenn.py:317-354) + the new left-orthonormal site tensor (lib/tenn.py:229-252).
@@ -902,7 +914,7 @@ __device__ __forceinline__ void jacobi_tail(const DqaDev& d, int inst, int l, in
     atomicAdd(&d.counters[inst * DQA_NCNT + 5],
               (unsigned long long)sweeps * (unsigned long long)(k * (k - 1) / 2) * 8ull * mr + nrot_total * 20ull * mr +
                   (unsigned long long)sweeps * 4ull * mr * k);
-    if (l == d.N - 1) d.bdmon[(size_t)inst * d.P * d.n_xi + (size_t)p_step * d.n_xi + mu] = bond[d.N / 2];
+    if (l == d.N - 1) d.bdmon[(size_t)inst * d.P * d.n_xi + (size_t)(p_step >= 0 ? p_step : *d.pdev) * d.n_xi + mu] = bond[d.N / 2];
   }
   __syncthreads();
   const int n_chi = sh_i[1];
@@ -1306,9 +1318,20 @@ __global__ void __launch_bounds__(RS * 32, RS >= 8 ? JSYS_MINB8 : (RS >= 6 ? 3 :
 // (lib/dQA_utils.py:26-30 + lib/tenn.py:67-81 for a bond-1 MPO), all sites in one launch.
 // grid (N, batch)
 // ---------------------------------------------------------------------------------
-__global__ void k_mixer(DqaDev d, double cb, double sb, double one_minus_s, int per_inst) {
+// mode 0: cb, sb as given; 1: per-instance dt, (1 - s_p) given; 2: step counter on the device (graph replay)
+__global__ void k_mixer(DqaDev d, double cb, double sb, double one_minus_s, int mode) {
   const int site = blockIdx.x, inst = blockIdx.y;
-  if (per_inst) {  // instances with their own dt: beta = (1 - s_p) * dt_inst (dQA_mps.py:88-89)
+  if (mode == 2) {
+    const int p = *d.pdev;
+    if (d.ntab > 1) {
+      one_minus_s = 1.0 - (double)(p + 1) / d.P;
+      mode = 1;
+    } else {
+      cb = d.mixtab[2 * p];
+      sb = d.mixtab[2 * p + 1];
+    }
+  }
+  if (mode == 1) {  // instances with their own dt: beta = (1 - s_p) * dt_inst (dQA_mps.py:88-89)
     const double beta = one_minus_s * d.dtv[inst];
     cb = cos(beta);
     sb = sin(beta);
@@ -1517,6 +1540,7 @@ __global__ void k_energy_ext_reduce(const cplx* tmk, const cplx* gk, int n_xi, i
 // eps = (1/N) sum_mu [ sum_{k<=D/2} g_k T_k + sum_{0<k<D/2} g_{D-k} conj(T_k) ]; one warp per instance
 __global__ void k_energy_reduce(DqaDev d, cplx* out, size_t stride) {
   const int inst = blockIdx.x, lane = threadIdx.x;
+  if (!out) out = d.eps + (*d.pdev + 1);  // graph replay: the slot of the step in flight
   cplx acc = cmk(0.0, 0.0);
   const int n = d.n_xi * d.kh;
   for (int i = lane; i < n; i += 32) {
@@ -1527,4 +1551,10 @@ __global__ void k_energy_reduce(DqaDev d, cplx* out, size_t stride) {
   }
   acc = warp_sum(acc);
   if (lane == 0) out[(size_t)inst * stride] = cscale(acc, 1.0 / d.N);
+}
+
+
+// end of a replayed step: advance the device step counter
+__global__ void k_advance(DqaDev d) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) *d.pdev += 1;
 }

@@ -325,6 +325,19 @@ static inline cudaError_t cudaPeekAtLastError() { return 0; }
 static inline cudaError_t cudaSetDevice(int) { return 0; }
 static inline cudaError_t cudaGetDevice(int* d) { *d = 0; return 0; }
 enum cudaDeviceAttr { cudaDevAttrMaxSharedMemoryPerBlockOptin = 97 };
+// CUDA graphs: not emulated (the plan never enables them in this build); the calls only have to compile
+typedef void* cudaGraph_t;
+typedef void* cudaGraphExec_t;
+enum cudaStreamCaptureMode { cudaStreamCaptureModeThreadLocal = 1 };
+static const unsigned cudaStreamNonBlocking = 1;
+static inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { *s = nullptr; return 0; }
+static inline cudaError_t cudaStreamDestroy(cudaStream_t) { return 0; }
+static inline cudaError_t cudaStreamBeginCapture(cudaStream_t, cudaStreamCaptureMode) { return 1; }
+static inline cudaError_t cudaStreamEndCapture(cudaStream_t, cudaGraph_t* g) { *g = nullptr; return 1; }
+static inline cudaError_t cudaGraphInstantiate(cudaGraphExec_t* e, cudaGraph_t, unsigned long long) { *e = nullptr; return 1; }
+static inline cudaError_t cudaGraphDestroy(cudaGraph_t) { return 0; }
+static inline cudaError_t cudaGraphExecDestroy(cudaGraphExec_t) { return 0; }
+static inline cudaError_t cudaGraphLaunch(cudaGraphExec_t, cudaStream_t) { return 1; }
 static inline cudaError_t cudaDeviceGetAttribute(int* v, cudaDeviceAttr, int) { *v = 227 * 1024; return 0; }
 static inline const char* cudaGetErrorString(cudaError_t) { return "emul"; }
 template <class F>

@@ -259,3 +259,43 @@ def extra():
 
 if __name__ == "__main__" and os.environ.get("EXTRA"):
     extra()
+
+
+def bipartite_rounds(k):
+    """Recursive bipartite ordering: level 0 pairs every column of the lower half with every column of the upper half
+    (k/2 rounds, one half circulating past the other), then both halves do the same inside themselves in parallel, and
+    so on: k/2 + k/4 + ... + 1 = k-1 rounds, k/2 disjoint pairs in every round.  (One column of every pair stays where it
+    is for a whole level: the ordering of a systolic array that keeps one column of the pair in registers and lets the
+    other circulate through shared memory by index arithmetic.)"""
+    rounds = []
+    size = k
+    while size >= 2:
+        h = size // 2
+        for r in range(h):
+            pairs = []
+            for base in range(0, k, size):
+                for i in range(h):
+                    pairs.append((base + i, base + h + (i + r) % h))
+            rounds.append(pairs)
+        size = h
+    return rounds
+
+
+def ordering_study():
+    mats = collect(32, want=16)
+    Ls = [lq_l(th) for th in mats]
+    k = 64
+    for name, rounds in (("odd-even (systolic kernel)", oddeven_rounds(k)), ("round robin", S.round_robin_pairs(k)),
+                         ("recursive bipartite", bipartite_rounds(k))):
+        seen = set()
+        for pr in rounds:
+            flat = [x for p in pr for x in p]
+            assert len(flat) == len(set(flat))
+            seen |= {tuple(sorted(p)) for p in pr}
+        out = [scalar_jacobi(L, rounds) for L in Ls]
+        print(f"{name:28s} rounds/sweep {len(rounds):3d} pairs {len(seen):5d}  sweeps {np.mean([o[1] for o in out]):5.2f} "
+              f"rot {np.mean([o[2] for o in out]):8.1f}  max|ds| {max(check(L, o[0]) for L, o in zip(Ls, out)):.1e}")
+
+
+if __name__ == "__main__" and os.environ.get("ORDERING"):
+    ordering_study()

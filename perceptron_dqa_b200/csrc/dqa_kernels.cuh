@@ -463,6 +463,10 @@ __device__ __forceinline__ void theta_gemm2(cplx* thc, int ld, int offo, int s, 
   }
 }
 
+// Measured and rejected (round 2): 2 x 2 register blocking of the two GEMMs (one task = 2 row tiles x 2 column tiles, NT + MT
+// fragment loads per 16 DMMAs instead of 3 per 8, aimed at the 82 % busy L1 data pipe).  98 registers instead of 56 cut the
+// resident CTAs per SM from 9 to 5 and the kernel got SLOWER: 92.6 vs 71.6 ms per step at chi=32, 107.6 vs 76.4 at chi=48
+// (batch 888 / 296).  The loads from global memory are hidden by warps in flight, not by fewer loads.
 // row stride of C in shared memory: = 4 (mod 8) complex, so the two rows a quarter-warp reads in one DMMA fragment load
 // (4 consecutive k each) do not share banks
 __host__ __device__ inline int theta_ldc(int chi) { return ((chi + 7) & ~7) + 4; }

@@ -63,7 +63,7 @@ def launches(tag):
     tot = sum(v[1] for v in agg.values())
     with open(os.path.join(PROF, f"{tag}_launch_shares.csv"), "w") as f:
         f.write(f"# {tag}: ncu launch list of `python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-roofline` "
-                f"(-s 5750 -c 1450: one dQA step of 888 realisations, N=21, chi=32)\n")
+                f"(one dQA step of 888 realisations, N=21, chi=32, skipping the warm-up launches)\n")
         f.write("# per-launch times under ncu are cold-cache and serialised: compare SHARES with bench.py's "
                 "roofline.families[*].share_of_step\n")
         f.write("kernel,launches,total_ms,share\n")
@@ -98,6 +98,17 @@ def main():
     copy(f"bench_{t}.json", f"{t}_bench.json")
     copy(f"bench_{t}_ref.json", f"{t}_bench_reference_arm.json")
     copy("bench_2gpu.json", f"{t}_bench_2gpu.json")
+    for n in (2, 4, 8):  # round 2 names
+        copy(f"{t}_bench_{n}gpu.json", f"{t}_bench_{n}gpu.json")
+        copy(f"{t}_c4_{n}gpu.json", f"{t}_c4_{n}gpu.json")
+    copy(f"{t}_c4_1gpu.json", f"{t}_c4_1gpu.json")
+    copy(f"{t}_c4_eps_mean_8gpu.npz", f"{t}_c4_eps_mean.npz")
+    copy(f"{t}_c5.json", f"{t}_c5.json")
+    copy(f"{t}_c5_batch74.json", f"{t}_c5_batch74.json")
+    copy(f"{t}_c2_full_runs.jsonl", f"{t}_c2_full_runs.jsonl")
+    copy(f"{t}_fp64_peaks.json", f"{t}_fp64_peaks.json")
+    copy(f"chi_sweep_{t}.jsonl", f"{t}_chi_sweep.jsonl")
+    copy(f"pytest_gpu_{t}.log", f"{t}_pytest_gpu.log")
     copy("free_run.log", f"{t}_free_run_vs_reference_envelope.txt")
     copy("parity_report.txt", f"{t}_teacher_forced_parity.txt")
     launches(t)

@@ -30,6 +30,12 @@ static void (*const KJ_Y3)(DqaDev, int, int, int) = k_jacobi_sys<3>;
 static void (*const KJ_Y4)(DqaDev, int, int, int) = k_jacobi_sys<4>;
 static void (*const KJ_Y6)(DqaDev, int, int, int) = k_jacobi_sys<6>;
 static void (*const KJ_Y8)(DqaDev, int, int, int) = k_jacobi_sys<8>;
+static void (*const KJ_Y10)(DqaDev, int, int, int) = k_jacobi_sys<10>;  // chi <= 40 .. 64: one CTA per SM, the factor still in registers
+static void (*const KJ_Y12)(DqaDev, int, int, int) = k_jacobi_sys<12>;
+#ifndef DQA_EMUL
+static void (*const KJ_C14)(DqaDev, int, int, int) = k_jacobi_sys_cl<14>;  // chi <= 56, 64: the systolic array on a cluster of two CTAs
+static void (*const KJ_C16)(DqaDev, int, int, int) = k_jacobi_sys_cl<16>;
+#endif
 
 struct dqa_handle {
   dqa_config cfg;
@@ -49,6 +55,8 @@ struct dqa_handle {
   bool use_graph = false, capturing = false;
   long long graph_nodes = 0;
   bool jac_sys;
+  int jac_sys_big = 2;  // systolic Jacobi above chi = 32 (DQA_JAC_SYS_BIG): 0 off; 1: chi <= 48 (one CTA per SM, 166 registers); 2: also 56 < chi <= 64 on a
+                        // cluster of two CTAs; 3: the cluster kernel for 48 < chi <= 56 too (measured slower than the shared-memory kernel there)
   char err[512];
   // profiling
   bool profiling;
@@ -260,6 +268,9 @@ extern "C" int dqa_create(dqa_t** out, const dqa_config* cfg) {
   {
     const char* env = getenv("DQA_JAC_SYS");  // 0: use the shared-memory-resident Jacobi for every chi
     h->jac_sys = !(env && atoi(env) == 0);
+    env = getenv("DQA_JAC_SYS_BIG");
+    if (env) h->jac_sys_big = atoi(env);
+    if (!h->jac_sys) h->jac_sys_big = 0;
   }
   DevGuard guard(c.device);
   {
@@ -276,6 +287,10 @@ extern "C" int dqa_create(dqa_t** out, const dqa_config* cfg) {
   DQA_OPTIN(k_sector_qr<8>); DQA_OPTIN(k_sector_qr<10>); DQA_OPTIN(k_sector_qr<12>); DQA_OPTIN(k_sector_qr<16>);
   DQA_OPTIN(KJ_0S); DQA_OPTIN(KJ_0G);
   DQA_OPTIN(KJ_Y2); DQA_OPTIN(KJ_Y3); DQA_OPTIN(KJ_Y4); DQA_OPTIN(KJ_Y6); DQA_OPTIN(KJ_Y8);
+  DQA_OPTIN(KJ_Y10); DQA_OPTIN(KJ_Y12);
+#ifndef DQA_EMUL
+  DQA_OPTIN(KJ_C14); DQA_OPTIN(KJ_C16);
+#endif
   DQA_OPTIN(k_lq); DQA_OPTIN(KE_1); DQA_OPTIN(KE_2); DQA_OPTIN(k_theta);
 #undef DQA_OPTIN
   return DQA_OK;
@@ -523,6 +538,13 @@ static int launch_truncate(dqa_t* h, int p, int mu) {
       else if (h->jac_sys && d.chi <= 16) HL(KJ_Y4, dim3(d.batch), dim3(t_sys), svd_smem(d.chi), h->stream, d, l, mu, p);
       else if (h->jac_sys && d.chi <= 24) HL(KJ_Y6, dim3(d.batch), dim3(t_sys), svd_smem(d.chi), h->stream, d, l, mu, p);
       else if (h->jac_sys && d.chi <= 32) HL(KJ_Y8, dim3(d.batch), dim3(t_sys), svd_smem(d.chi), h->stream, d, l, mu, p);
+      else if (h->jac_sys_big && d.chi <= 40) HL(KJ_Y10, dim3(d.batch), dim3(t_sys), svd_smem(d.chi), h->stream, d, l, mu, p);
+      else if (h->jac_sys_big && d.chi <= 48) HL(KJ_Y12, dim3(d.batch), dim3(t_sys), svd_smem(d.chi), h->stream, d, l, mu, p);
+#ifndef DQA_EMUL
+      // 48 < chi <= 56 stays on the shared-memory kernel (L fits there; the cluster build was measured 2 % slower at chi = 56)
+      else if (h->jac_sys_big > 2 && d.chi <= 56) HL(KJ_C14, dim3(2 * d.batch), dim3(32 * ((8 * ((d.chi + 1) / 2) + 31) / 32)), svd_cl_smem(d.chi), h->stream, d, l, mu, p);
+      else if (h->jac_sys_big > 1 && d.chi > 56 && d.chi <= 64) HL(KJ_C16, dim3(2 * d.batch), dim3(32 * ((8 * ((d.chi + 1) / 2) + 31) / 32)), svd_cl_smem(d.chi), h->stream, d, l, mu, p);
+#endif
       else if (svd_l_in_smem(d.chi)) HL(KJ_0S, dim3(d.batch), dim3(h->t_svd), svd_smem(d.chi), h->stream, d, l, mu, p);
       else HL(KJ_0G, dim3(d.batch), dim3(h->t_svd), svd_smem(d.chi), h->stream, d, l, mu, p);
     }

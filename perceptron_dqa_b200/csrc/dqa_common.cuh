@@ -12,6 +12,8 @@
 #define DQA_DYN_SMEM(name) char* name = ::emul::dyn_smem_
 #else
 #include <cuda_runtime.h>
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
 #define DQA_LAUNCH(kernel, grid, block, smem, stream, ...) \
   kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
 #define DQA_DYN_SMEM(name) extern __shared__ __align__(16) char name[]

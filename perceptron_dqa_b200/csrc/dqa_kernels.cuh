@@ -527,10 +527,12 @@ __host__ __device__ inline int lq_npad(int ncols) { return ((ncols + 7) & ~7) + 
 __host__ __device__ inline size_t lq_smem(int qmax, int chi, int pb) {
   return sizeof(cplx) * ((size_t)pb * lq_npad(qmax) + 2 * LQ_PB * LQ_PB + LQ_PB + (size_t)LQ_MAXW * 64 + (size_t)((2 * chi + 7) / 8) * 64);
 }
-// panel height: 8 rows unless the panel (pb x qmax) would not leave room for two CTAs per SM / fit at all
+// panel height: 8 rows while such a panel (pb x qmax) leaves room for two CTAs per SM; wider Theta (N=64, chi=64: 3 776
+// columns) takes the tallest panel that still fits one CTA (3 rows there; the power-of-two search of round 1 gave 2)
 __host__ __device__ inline int lq_pick_pb(int qmax, int chi) {
+  if (lq_smem(qmax, chi, LQ_PB) <= 180 * 1024) return LQ_PB;
   int pb = LQ_PB;
-  while (pb > 1 && lq_smem(qmax, chi, pb) > 180 * 1024) pb >>= 1;
+  while (pb > 1 && lq_smem(qmax, chi, pb) > 224 * 1024) pb -= 1;
   return pb;
 }
 
@@ -833,7 +835,7 @@ __device__ __forceinline__ void rr_pair(int n, int round, int idx, int& p, int& 
 
 // Shared tail of the Jacobi kernels: singular values of the kc stored columns (k of them real, kc - k zero padding),
 // ordering, the reference's trim rule (lib/tenn.py:317-354), counters, and the new left-orthonormal site tensor.
-__device__ __forceinline__ void jacobi_tail(const DqaDev& d, int inst, int l, int mu, int p_step, const cplx* L, int ldl, int mr, int k,
+__device__ __noinline__ void jacobi_tail(const DqaDev& d, int inst, int l, int mu, int p_step, const cplx* L, int ldl, int mr, int k,
                                             int kc, double* sig, double* ssorted, int* order, int* sh_i, int* bond, int converged,
                                             int sweeps, unsigned long long nrot_total) {
   const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarp = nt >> 5;
@@ -1145,7 +1147,7 @@ __global__ void __launch_bounds__(512) k_jacobi(DqaDev d, int l, int mu, int p_s
 #define JSYS_MINB8 2  // CTAs per SM the 8-row-slot systolic Jacobi is compiled for
 #endif
 template <int RS>
-__global__ void __launch_bounds__(RS * 32, RS >= 8 ? JSYS_MINB8 : (RS >= 6 ? 3 : (RS >= 4 ? 6 : 8))) k_jacobi_sys(DqaDev d, int l, int mu, int p_step) {
+__global__ void __launch_bounds__(RS * 32, RS > 8 ? 1 : (RS == 8 ? JSYS_MINB8 : (RS >= 6 ? 3 : (RS >= 4 ? 6 : 8)))) k_jacobi_sys(DqaDev d, int l, int mu, int p_step) {
   DQA_DYN_SMEM(smraw);
   const int inst = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
   const int chi = d.chi;
@@ -1316,6 +1318,208 @@ __global__ void __launch_bounds__(RS * 32, RS >= 8 ? JSYS_MINB8 : (RS >= 6 ? 3 :
   __syncthreads();
   jacobi_tail(d, inst, l, mu, p_step, X, mr, mr, k, kp, sig, ssorted, order, sh_i, bond, converged, sweeps, nrot_total);
 }
+
+#ifndef DQA_EMUL
+// ---------------------------------------------------------------------------------
+// k_jacobi_sys_cl: the systolic array of k_jacobi_sys spread over a CLUSTER OF TWO CTAs (two SMs), for 2chi = 112 / 128
+// rows (chi = 56, 64): at RS = 14 / 16 rows per lane the two register-resident columns of a group take 112 / 128
+// registers, so the 56 / 64 groups of one SVD do not fit the register file of one SM (the one-CTA build spills and was
+// measured slower than the shared-memory kernel).  Each CTA runs half of the line of groups; the column a group passes
+// to its ring neighbour is stored straight into the neighbour's exchange slot -- in this CTA's shared memory or, for the
+// two groups at the seam and the wrap-around, in the partner's (distributed shared memory) -- and the per-round
+// block barrier becomes a cluster barrier.  The converged columns are parked in global memory (lbuf, L2-resident) and
+// CTA 0 runs the common tail (ordering, the reference's trim rule, new site tensor).
+// shared (per CTA): exchange buffers 2 x (groups/2 x mr) | sig | xn/ssorted | order | sh_i
+// ---------------------------------------------------------------------------------
+__host__ __device__ inline size_t svd_cl_smem(int chi) {
+  const int gl = (chi + 1) / 2;  // groups per CTA
+  return sizeof(cplx) * (size_t)2 * gl * (2 * chi) + sizeof(double) * (4 * chi + 8) + sizeof(int) * (2 * chi + 8);
+}
+
+template <int RS>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(RS * 16, 1) k_jacobi_sys_cl(DqaDev d, int l, int mu, int p_step) {
+  DQA_DYN_SMEM(smraw);
+  cg::cluster_group cluster = cg::this_cluster();
+  const int crank = (int)cluster.block_rank();
+  const int inst = blockIdx.x >> 1, tid = threadIdx.x, lane = tid & 31;
+  const int chi = d.chi;
+  const int GL = (chi + 1) / 2;  // groups per CTA (blockDim.x = 8 * GL rounded up to a warp)
+  cplx* lglob = d.lbuf + (size_t)inst * (size_t)(2 * chi) * (2 * chi);
+  cplx* X = (cplx*)smraw;
+  double* sig = (double*)(smraw + sizeof(cplx) * (size_t)2 * GL * (2 * chi));
+  double* ssorted = sig + 2 * chi;
+  int* order = (int*)(ssorted + 2 * chi + 8);
+  int* sh_i = order + 2 * chi;  // [0]=rotation count, [1]=n_chi, [2]=some rotated pair was above the quadratic threshold
+  int* bond = d.bond + inst * (d.N + 1);
+  const int mr = 2 * bond[l];
+  const int* qd1 = d.qdim + ((size_t)inst * (d.N + 1) + (l + 1)) * d.smax;
+  const int Q = qdim_prefix(qd1, d.N - l);
+  const int k = mr < Q ? mr : Q;
+  const int kp = k + (k & 1), h = kp >> 1;  // h groups hold the kp columns
+  const int gloc = tid >> 3, li = lane & 7;
+  const int g = crank * GL + gloc;           // position in the line of groups
+  const bool act = gloc < GL && g < h;
+  double* xn = ssorted;  // [2][GL] squared norms in flight
+
+  cplx A[RS], B[RS];
+#pragma unroll
+  for (int t = 0; t < RS; ++t) {
+    const int r = li + 8 * t;
+    const bool in = act && r < mr;
+    B[t] = (in && 2 * g < k) ? lglob[r + (size_t)(2 * g) * (2 * chi)] : cmk(0.0, 0.0);
+    A[t] = (in && 2 * g + 1 < k) ? lglob[r + (size_t)(2 * g + 1) * (2 * chi)] : cmk(0.0, 0.0);
+  }
+  // ring neighbours and where their exchange slots live
+  const int gr = (g + 1 < h) ? g + 1 : 0, gl = (g > 0) ? g - 1 : h - 1;
+  cplx* Xr = cluster.map_shared_rank(X, gr / GL);
+  cplx* Xl = cluster.map_shared_rank(X, gl / GL);
+  double* xnr = cluster.map_shared_rank(xn, gr / GL);
+  double* xnl = cluster.map_shared_rank(xn, gl / GL);
+  const int sr = gr % GL, sl = gl % GL;
+  const size_t bufsz = (size_t)GL * mr;
+  const double tol = sqrt((double)mr) * 2.220446049250313e-16, tol2 = tol * tol;
+  int sweeps = 0, converged = (k <= 1);
+  unsigned long long nrot_total = 0;
+  int* sh_other = cluster.map_shared_rank(sh_i, crank ^ 1);
+  cluster.sync();  // both CTAs are resident before anybody stores into the partner's shared memory
+  for (int sweep = 0; sweep < d.max_sweeps && !converged; ++sweep) {
+    double nA = 0.0, nB = 0.0;
+#pragma unroll
+    for (int t = 0; t < RS; ++t) {
+      nA += cabs2(A[t]);
+      nB += cabs2(B[t]);
+    }
+    nA += __shfl_xor_sync(DQA_FULL, nA, 4);
+    nB += __shfl_xor_sync(DQA_FULL, nB, 4);
+    nA += __shfl_xor_sync(DQA_FULL, nA, 2);
+    nB += __shfl_xor_sync(DQA_FULL, nB, 2);
+    nA += __shfl_xor_sync(DQA_FULL, nA, 1);
+    nB += __shfl_xor_sync(DQA_FULL, nB, 1);
+    if (tid == 0) {
+      sh_i[0] = 0;
+      sh_i[2] = 0;
+    }
+    int myrot = 0, mybig = 0;
+    for (int round = 0; round < kp; ++round) {
+      const bool straddle = round & 1;
+      const bool idle = straddle && g == 0;
+      cplx g0 = cmk(0.0, 0.0), g1 = cmk(0.0, 0.0);
+#pragma unroll
+      for (int t = 0; t < RS; t += 2) {
+        g0 = cfmac(B[t], A[t], g0);
+        if (t + 1 < RS) g1 = cfmac(B[t + 1], A[t + 1], g1);
+      }
+      cplx gd = cadd(g0, g1);
+      gd.x += __shfl_xor_sync(DQA_FULL, gd.x, 4);
+      gd.y += __shfl_xor_sync(DQA_FULL, gd.y, 4);
+      gd.x += __shfl_xor_sync(DQA_FULL, gd.x, 2);
+      gd.y += __shfl_xor_sync(DQA_FULL, gd.y, 2);
+      gd.x += __shfl_xor_sync(DQA_FULL, gd.x, 1);
+      gd.y += __shfl_xor_sync(DQA_FULL, gd.y, 1);
+      double c = 1.0;
+      cplx z1 = cmk(0.0, 0.0), z2 = cmk(0.0, 0.0);
+      int rot = 0;
+      if (idle && act) {
+        c = 0.0;
+        z1 = cmk(1.0, 0.0);
+        z2 = cmk(1.0, 0.0);
+        const double tn = nA;
+        nA = nB;
+        nB = tn;
+        rot = 1;
+      } else if (act) {
+        const double ag2 = cabs2(gd);
+        if (ag2 > tol2 * nA * nB && ag2 > 0.0) {
+          const double dl = 0.5 * (nB - nA), ad = fabs(dl);
+          const double r2 = fma(dl, dl, ag2);
+          const double r = r2 * rsqrt(r2);
+          const double u = r + ad;
+          const double q = rsqrt(2.0 * r * u);
+          c = u * q;
+          const double sq = copysign(q, dl);
+          z1 = cmk(-sq * gd.x, sq * gd.y);
+          z2 = cmk(sq * gd.x, sq * gd.y);
+          const double tg = copysign(2.0 * ag2 * r * q * q, dl);
+          if (ag2 > d.jac_quad2 * nA * nB) mybig = 1;
+          nA -= tg;
+          nB += tg;
+          nA = nA > 0.0 ? nA : 0.0;
+          nB = nB > 0.0 ? nB : 0.0;
+          rot = 1;
+          if (li == 0) myrot++;
+        }
+      }
+      if (__any_sync(DQA_FULL, rot)) {
+#pragma unroll
+        for (int t = 0; t < RS; ++t) {
+          const cplx a_ = A[t], b_ = B[t];
+          A[t] = cfma(z1, b_, cscale(a_, c));
+          B[t] = cfma(z2, a_, cscale(b_, c));
+        }
+      }
+      // ---- pass one column on: B to the right after an even round, A back to the left after an odd one ----
+      const size_t boff = straddle ? bufsz : 0;
+      const int noff = straddle ? GL : 0;
+      if (!straddle) {
+        if (act) {
+          cplx* dst = Xr + boff + (size_t)sr * mr;
+#pragma unroll
+          for (int t = 0; t < RS; ++t)
+            if (li + 8 * t < mr) dst[li + 8 * t] = B[t];
+          if (li == 0) xnr[noff + sr] = nB;
+        }
+        cluster.sync();
+        if (act) {
+          const cplx* src = X + boff + (size_t)gloc * mr;
+#pragma unroll
+          for (int t = 0; t < RS; ++t)
+            if (li + 8 * t < mr) B[t] = src[li + 8 * t];
+          nB = xn[noff + gloc];
+        }
+      } else {
+        if (act) {
+          cplx* dst = Xl + boff + (size_t)sl * mr;
+#pragma unroll
+          for (int t = 0; t < RS; ++t)
+            if (li + 8 * t < mr) dst[li + 8 * t] = A[t];
+          if (li == 0) xnl[noff + sl] = nA;
+        }
+        cluster.sync();
+        if (act) {
+          const cplx* src = X + boff + (size_t)gloc * mr;
+#pragma unroll
+          for (int t = 0; t < RS; ++t)
+            if (li + 8 * t < mr) A[t] = src[li + 8 * t];
+          nA = xn[noff + gloc];
+        }
+      }
+    }
+    if (myrot) atomicAdd(&sh_i[0], myrot);
+    if (mybig) atomicOr(&sh_i[2], 1);
+    cluster.sync();
+    sweeps++;
+    const int rot_all = sh_i[0] + sh_other[0], big_all = sh_i[2] | sh_other[2];
+    nrot_total += (unsigned long long)rot_all;
+    converged = (rot_all == 0) || (big_all == 0);  // same rule as k_jacobi
+    cluster.sync();  // the partner has read this CTA's counters before they are reset
+  }
+  // ---- park the columns in global memory (any order: the tail sorts by singular value) ----
+  if (act) {
+#pragma unroll
+    for (int t = 0; t < RS; ++t) {
+      const int r = li + 8 * t;
+      if (r < mr) {
+        lglob[r + (size_t)(2 * g) * (2 * chi)] = B[t];
+        lglob[r + (size_t)(2 * g + 1) * (2 * chi)] = A[t];
+      }
+    }
+  }
+  __threadfence();
+  cluster.sync();
+  if (crank != 0) return;  // no distributed-shared-memory access happens after the barrier above
+  jacobi_tail(d, inst, l, mu, p_step, lglob, 2 * chi, mr, k, kp, sig, ssorted, order, sh_i, bond, converged, sweeps, nrot_total);
+}
+#endif  // DQA_EMUL
 
 // ---------------------------------------------------------------------------------
 // k_mixer: A[a,s',c] <- sum_s u[s',s] A[a,s,c], u = [[cos b, i sin b],[i sin b, cos b]]

@@ -31,6 +31,7 @@ struct int2 { int x, y; };
 #define __device__
 #define __host__
 #define __forceinline__ inline
+#define __noinline__
 #define __restrict__
 #define __shared__ static
 #define __launch_bounds__(...)

@@ -33,8 +33,7 @@ static void (*const KJ_Y8)(DqaDev, int, int, int) = k_jacobi_sys<8>;
 static void (*const KJ_Y10)(DqaDev, int, int, int) = k_jacobi_sys<10>;  // chi <= 40 .. 64: one CTA per SM, the factor still in registers
 static void (*const KJ_Y12)(DqaDev, int, int, int) = k_jacobi_sys<12>;
 #ifndef DQA_EMUL
-static void (*const KJ_C14)(DqaDev, int, int, int) = k_jacobi_sys_cl<14>;  // chi <= 56, 64: the systolic array on a cluster of two CTAs
-static void (*const KJ_C16)(DqaDev, int, int, int) = k_jacobi_sys_cl<16>;
+static void (*const KJ_C16)(DqaDev, int, int, int) = k_jacobi_sys_cl<16, 2, 1>;  // 56 < chi <= 64: the systolic array on a cluster of two CTAs
 #endif
 
 struct dqa_handle {
@@ -55,8 +54,7 @@ struct dqa_handle {
   bool use_graph = false, capturing = false;
   long long graph_nodes = 0;
   bool jac_sys;
-  int jac_sys_big = 2;  // systolic Jacobi above chi = 32 (DQA_JAC_SYS_BIG): 0 off; 1: chi <= 48 (one CTA per SM, 166 registers); 2: also 56 < chi <= 64 on a
-                        // cluster of two CTAs; 3: the cluster kernel for 48 < chi <= 56 too (measured slower than the shared-memory kernel there)
+  int jac_sys_big = 2;  // systolic Jacobi above chi = 32 (DQA_JAC_SYS_BIG): 0 off; 1: chi <= 48 (one CTA per SM, 166 registers); 2: also 56 < chi <= 64 on a cluster of two CTAs
   char err[512];
   // profiling
   bool profiling;
@@ -289,7 +287,7 @@ extern "C" int dqa_create(dqa_t** out, const dqa_config* cfg) {
   DQA_OPTIN(KJ_Y2); DQA_OPTIN(KJ_Y3); DQA_OPTIN(KJ_Y4); DQA_OPTIN(KJ_Y6); DQA_OPTIN(KJ_Y8);
   DQA_OPTIN(KJ_Y10); DQA_OPTIN(KJ_Y12);
 #ifndef DQA_EMUL
-  DQA_OPTIN(KJ_C14); DQA_OPTIN(KJ_C16);
+  DQA_OPTIN(KJ_C16);
 #endif
   DQA_OPTIN(k_lq); DQA_OPTIN(KE_1); DQA_OPTIN(KE_2); DQA_OPTIN(k_theta);
 #undef DQA_OPTIN
@@ -541,9 +539,8 @@ static int launch_truncate(dqa_t* h, int p, int mu) {
       else if (h->jac_sys_big && d.chi <= 40) HL(KJ_Y10, dim3(d.batch), dim3(t_sys), svd_smem(d.chi), h->stream, d, l, mu, p);
       else if (h->jac_sys_big && d.chi <= 48) HL(KJ_Y12, dim3(d.batch), dim3(t_sys), svd_smem(d.chi), h->stream, d, l, mu, p);
 #ifndef DQA_EMUL
-      // 48 < chi <= 56 stays on the shared-memory kernel (L fits there; the cluster build was measured 2 % slower at chi = 56)
-      else if (h->jac_sys_big > 2 && d.chi <= 56) HL(KJ_C14, dim3(2 * d.batch), dim3(32 * ((8 * ((d.chi + 1) / 2) + 31) / 32)), svd_cl_smem(d.chi), h->stream, d, l, mu, p);
-      else if (h->jac_sys_big > 1 && d.chi > 56 && d.chi <= 64) HL(KJ_C16, dim3(2 * d.batch), dim3(32 * ((8 * ((d.chi + 1) / 2) + 31) / 32)), svd_cl_smem(d.chi), h->stream, d, l, mu, p);
+      // 48 < chi <= 56 stays on the shared-memory kernel: L fits there, and the cluster build was measured 2 % slower at chi = 56
+      else if (h->jac_sys_big > 1 && d.chi > 56 && d.chi <= 64) HL(KJ_C16, dim3(2 * d.batch), dim3(32 * ((8 * ((d.chi + 1) / 2) + 31) / 32)), svd_cl_smem(d.chi, 2), h->stream, d, l, mu, p);
 #endif
       else if (svd_l_in_smem(d.chi)) HL(KJ_0S, dim3(d.batch), dim3(h->t_svd), svd_smem(d.chi), h->stream, d, l, mu, p);
       else HL(KJ_0G, dim3(d.batch), dim3(h->t_svd), svd_smem(d.chi), h->stream, d, l, mu, p);

@@ -1331,19 +1331,19 @@ __global__ void __launch_bounds__(RS * 32, RS > 8 ? 1 : (RS == 8 ? JSYS_MINB8 : 
 // CTA 0 runs the common tail (ordering, the reference's trim rule, new site tensor).
 // shared (per CTA): exchange buffers 2 x (groups/2 x mr) | sig | xn/ssorted | order | sh_i
 // ---------------------------------------------------------------------------------
-__host__ __device__ inline size_t svd_cl_smem(int chi) {
-  const int gl = (chi + 1) / 2;  // groups per CTA
+__host__ __device__ inline size_t svd_cl_smem(int chi, int cs) {
+  const int gl = (chi + cs - 1) / cs;  // groups per CTA
   return sizeof(cplx) * (size_t)2 * gl * (2 * chi) + sizeof(double) * (4 * chi + 8) + sizeof(int) * (2 * chi + 8);
 }
 
-template <int RS>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(RS * 16, 1) k_jacobi_sys_cl(DqaDev d, int l, int mu, int p_step) {
+template <int RS, int CS, int MINB>  // CS CTAs per cluster (one SVD on CS SMs), MINB CTAs (of different SVDs) resident per SM
+__global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(RS * 32 / CS, MINB) k_jacobi_sys_cl(DqaDev d, int l, int mu, int p_step) {
   DQA_DYN_SMEM(smraw);
   cg::cluster_group cluster = cg::this_cluster();
   const int crank = (int)cluster.block_rank();
-  const int inst = blockIdx.x >> 1, tid = threadIdx.x, lane = tid & 31;
+  const int inst = blockIdx.x / CS, tid = threadIdx.x, lane = tid & 31;
   const int chi = d.chi;
-  const int GL = (chi + 1) / 2;  // groups per CTA (blockDim.x = 8 * GL rounded up to a warp)
+  const int GL = (chi + CS - 1) / CS;  // groups per CTA (blockDim.x = 8 * GL rounded up to a warp)
   cplx* lglob = d.lbuf + (size_t)inst * (size_t)(2 * chi) * (2 * chi);
   cplx* X = (cplx*)smraw;
   double* sig = (double*)(smraw + sizeof(cplx) * (size_t)2 * GL * (2 * chi));
@@ -1380,8 +1380,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(RS * 16, 1) k_jacobi
   const double tol = sqrt((double)mr) * 2.220446049250313e-16, tol2 = tol * tol;
   int sweeps = 0, converged = (k <= 1);
   unsigned long long nrot_total = 0;
-  int* sh_other = cluster.map_shared_rank(sh_i, crank ^ 1);
-  cluster.sync();  // both CTAs are resident before anybody stores into the partner's shared memory
+  cluster.sync();  // all CTAs of the cluster are resident before anybody stores into the partner's shared memory
   for (int sweep = 0; sweep < d.max_sweeps && !converged; ++sweep) {
     double nA = 0.0, nB = 0.0;
 #pragma unroll
@@ -1498,7 +1497,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(RS * 16, 1) k_jacobi
     if (mybig) atomicOr(&sh_i[2], 1);
     cluster.sync();
     sweeps++;
-    const int rot_all = sh_i[0] + sh_other[0], big_all = sh_i[2] | sh_other[2];
+    int rot_all = 0, big_all = 0;
+#pragma unroll
+    for (int rk = 0; rk < CS; ++rk) {
+      const int* sh_r = cluster.map_shared_rank(sh_i, rk);
+      rot_all += sh_r[0];
+      big_all |= sh_r[2];
+    }
     nrot_total += (unsigned long long)rot_all;
     converged = (rot_all == 0) || (big_all == 0);  // same rule as k_jacobi
     cluster.sync();  // the partner has read this CTA's counters before they are reset

@@ -300,7 +300,8 @@ def run_ours(a):
         pl.step(1)
         ev[k][1].record()
     barrier()
-    ms = sum(x.elapsed_time(y) for x, y in ev)
+    ms_steps = [x.elapsed_time(y) for x, y in ev]
+    ms = sum(ms_steps)
     launches = pl.launch_count() - l0
     clocks = sampler.summary()
     t = torch.tensor([ms], dtype=torch.float64, device=f"cuda:{local}")
@@ -353,7 +354,8 @@ def run_ours(a):
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": W,
-        "ms_per_step": ms_max / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": ms_max / a.steps, "ms_of_each_step_rank0": [round(v, 2) for v in ms_steps],
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "complex128", "data": "synthetic",
         "config": {"workload": workload_name(a, B, world), "batch_per_gpu": B,
                    "l2": "flushed (256 MiB write) between timed steps; per-step working set "

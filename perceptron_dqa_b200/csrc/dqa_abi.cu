@@ -33,7 +33,7 @@ static void (*const KJ_Y8)(DqaDev, int, int, int) = k_jacobi_sys<8>;
 static void (*const KJ_Y10)(DqaDev, int, int, int) = k_jacobi_sys<10>;  // chi <= 40 .. 64: one CTA per SM, the factor still in registers
 static void (*const KJ_Y12)(DqaDev, int, int, int) = k_jacobi_sys<12>;
 #ifndef DQA_EMUL
-static void (*const KJ_C16)(DqaDev, int, int, int) = k_jacobi_sys_cl<16, 2, 1>;  // 56 < chi <= 64: the systolic array on a cluster of two CTAs
+static void (*const KJ_C16)(DqaDev, int, int, int) = k_jacobi_sys_cl<16, 2, 1, 8>;  // 56 < chi <= 64: the systolic array on a cluster of two CTAs
 #endif
 
 struct dqa_handle {

@@ -833,9 +833,83 @@ __device__ __forceinline__ void rr_pair(int n, int round, int idx, int& p, int& 
   }
 }
 
+// The trimming decision of _trim_and_renorm_svd_result (lib/tenn.py:317-354) with the plan's policy; the reference's call
+// site (lib/tenn.py:238) fixes cutoff 1e-10, mode 4 (relative cumulative s^2), renorm 2, absorb right.  One
+// thread of the (out-of-line) tail.
+__device__ __forceinline__ void trim_policy(const double* ssorted, int k, int chi, double cutoff, int mode, int renorm, int converged,
+                                         int* n_chi_out, double* sc_out, double* discw_out, int* st_out) {
+  const bool pw2 = (mode == 3 || mode == 4 || mode < 3);
+  double tot = 0.0, tot2 = 0.0;
+  for (int i = 0; i < k; ++i) {
+    tot2 += ssorted[i] * ssorted[i];
+    tot += pw2 ? ssorted[i] * ssorted[i] : ssorted[i];
+  }
+  double csp = 0.0, ckeep = 0.0, ckeep2 = 0.0;
+  int cnt = 0, n_chi;
+  if (cutoff > 0.0 || renorm > 0) {
+    if (mode == 1) {
+      for (int i = 0; i < k; ++i) cnt += ssorted[i] > cutoff;
+      n_chi = cnt;
+    } else if (mode == 2) {
+      for (int i = 0; i < k; ++i) cnt += ssorted[i] > cutoff * ssorted[0];
+      n_chi = cnt;
+    } else {
+      const double thr = (1.0 - cutoff) * tot;
+      for (int i = 0; i < k; ++i) {
+        csp += pw2 ? ssorted[i] * ssorted[i] : ssorted[i];
+        if (mode == 4 || mode == 6) cnt += csp < thr;
+        else cnt += (tot - csp) > cutoff;
+      }
+      n_chi = cnt + 1;
+    }
+    if (n_chi < 1) n_chi = 1;
+    if (n_chi > chi) n_chi = chi;
+  } else {
+    n_chi = chi;
+  }
+  if (n_chi > k) n_chi = k;
+  for (int i = 0; i < n_chi; ++i) {
+    ckeep += pw2 ? ssorted[i] * ssorted[i] : ssorted[i];
+    ckeep2 += ssorted[i] * ssorted[i];
+  }
+  double sc = 1.0;
+  int st = 0;
+  if (!(tot2 == tot2) || tot2 > 1e300) st |= DQA_ST_NONFINITE;
+  if (tot2 == 0.0) st |= DQA_ST_ZERONORM;
+  if (!converged) st |= DQA_ST_NOCONV;
+  if (n_chi < k && ckeep > 0.0 && renorm > 0 && mode >= 3) sc = pw2 ? sqrt(tot / ckeep) : tot / ckeep;
+  *n_chi_out = n_chi;
+  *sc_out = sc;
+  *discw_out = tot2 > 0.0 ? (tot2 - ckeep2) / tot2 : 0.0;
+  *st_out = st;
+}
+
 // Shared tail of the Jacobi kernels: singular values of the kc stored columns (k of them real, kc - k zero padding),
 // ordering, the reference's trim rule (lib/tenn.py:317-354), counters, and the new left-orthonormal site tensor.
-__device__ __noinline__ void jacobi_tail(const DqaDev& d, int inst, int l, int mu, int p_step, const cplx* L, int ldl, int mr, int k,
+// what the tail needs of the plan, passed BY VALUE to an out-of-line function: taking the address of the kernel's DqaDev
+// parameter would force a 288-byte stack copy of it in every kernel that calls the tail (measured +9 % on the chi=10 Jacobi),
+// while inlining the tail perturbs the allocation of the round loops (+3.5 % on the chi=32 one)
+struct JacTailArgs {
+  cplx* mps;
+  double* schmidt;
+  int* nsv;
+  double* scale;
+  int* status;
+  unsigned long long* counters;
+  int* bdmon;
+  double* discw;
+  const int* pdev;
+  double cutoff;
+  int N, P, n_xi, chi, cutoff_mode, renorm;
+};
+__device__ __forceinline__ JacTailArgs jac_tail_args(const DqaDev& d) {
+  JacTailArgs a;
+  a.mps = d.mps; a.schmidt = d.schmidt; a.nsv = d.nsv; a.scale = d.scale; a.status = d.status; a.counters = d.counters;
+  a.bdmon = d.bdmon; a.discw = d.discw; a.pdev = d.pdev; a.cutoff = d.cutoff;
+  a.N = d.N; a.P = d.P; a.n_xi = d.n_xi; a.chi = d.chi; a.cutoff_mode = d.cutoff_mode; a.renorm = d.renorm;
+  return a;
+}
+__device__ __noinline__ void jacobi_tail(const JacTailArgs d, int inst, int l, int mu, int p_step, const cplx* L, int ldl, int mr, int k,
                                             int kc, double* sig, double* ssorted, int* order, int* sh_i, int* bond, int converged,
                                             int sweeps, unsigned long long nrot_total) {
   const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarp = nt >> 5;
@@ -865,50 +939,10 @@ __device__ __noinline__ void jacobi_tail(const DqaDev& d, int inst, int l, int m
   }
   __syncthreads();
   if (tid == 0) {
-    // _trim_and_renorm_svd_result (lib/tenn.py:317-354) with the plan's policy; the reference's call site
-    // (lib/tenn.py:238) fixes cutoff 1e-10, mode 4 (relative cumulative s^2), renorm 2, absorb right
-    const int mode = d.cutoff_mode;
-    const bool pw2 = (mode == 3 || mode == 4 || mode < 3);
-    double tot = 0.0, tot2 = 0.0;
-    for (int i = 0; i < k; ++i) {
-      tot2 += ssorted[i] * ssorted[i];
-      tot += pw2 ? ssorted[i] * ssorted[i] : ssorted[i];
-    }
-    double csp = 0.0, ckeep = 0.0, ckeep2 = 0.0;
-    int cnt = 0, n_chi;
-    if (d.cutoff > 0.0 || d.renorm > 0) {
-      if (mode == 1) {
-        for (int i = 0; i < k; ++i) cnt += ssorted[i] > d.cutoff;
-        n_chi = cnt;
-      } else if (mode == 2) {
-        for (int i = 0; i < k; ++i) cnt += ssorted[i] > d.cutoff * ssorted[0];
-        n_chi = cnt;
-      } else {
-        const double thr = (1.0 - d.cutoff) * tot;
-        for (int i = 0; i < k; ++i) {
-          csp += pw2 ? ssorted[i] * ssorted[i] : ssorted[i];
-          if (mode == 4 || mode == 6) cnt += csp < thr;
-          else cnt += (tot - csp) > d.cutoff;
-        }
-        n_chi = cnt + 1;
-      }
-      if (n_chi < 1) n_chi = 1;
-      if (n_chi > chi) n_chi = chi;
-    } else {
-      n_chi = chi;
-    }
-    if (n_chi > k) n_chi = k;
-    for (int i = 0; i < n_chi; ++i) {
-      ckeep += pw2 ? ssorted[i] * ssorted[i] : ssorted[i];
-      ckeep2 += ssorted[i] * ssorted[i];
-    }
-    double sc = 1.0;
-    int st = 0;
-    if (!(tot2 == tot2) || tot2 > 1e300) st |= DQA_ST_NONFINITE;
-    if (tot2 == 0.0) st |= DQA_ST_ZERONORM;
-    if (!converged) st |= DQA_ST_NOCONV;
-    if (n_chi < k && ckeep > 0.0 && d.renorm > 0 && mode >= 3) sc = pw2 ? sqrt(tot / ckeep) : tot / ckeep;
-    d.discw[(size_t)inst * d.N + l] = tot2 > 0.0 ? (tot2 - ckeep2) / tot2 : 0.0;
+    int n_chi, st;
+    double sc, dw;
+    trim_policy(ssorted, k, chi, d.cutoff, d.cutoff_mode, d.renorm, converged, &n_chi, &sc, &dw, &st);
+    d.discw[(size_t)inst * d.N + l] = dw;
     if (st) atomicOr(&d.status[inst], st);
     sh_i[1] = n_chi;
     d.scale[inst] = sc;
@@ -1124,7 +1158,7 @@ __global__ void __launch_bounds__(512) k_jacobi(DqaDev d, int l, int mu, int p_s
     }
     __syncthreads();
   }
-  jacobi_tail(d, inst, l, mu, p_step, L, ldl, mr, k, k, sig, ssorted, order, sh_i, bond, converged, sweeps, nrot_total);
+  jacobi_tail(jac_tail_args(d), inst, l, mu, p_step, L, ldl, mr, k, k, sig, ssorted, order, sh_i, bond, converged, sweeps, nrot_total);
 }
 
 // ---------------------------------------------------------------------------------
@@ -1316,7 +1350,7 @@ __global__ void __launch_bounds__(RS * 32, RS > 8 ? 1 : (RS == 8 ? JSYS_MINB8 : 
     }
   }
   __syncthreads();
-  jacobi_tail(d, inst, l, mu, p_step, X, mr, mr, k, kp, sig, ssorted, order, sh_i, bond, converged, sweeps, nrot_total);
+  jacobi_tail(jac_tail_args(d), inst, l, mu, p_step, X, mr, mr, k, kp, sig, ssorted, order, sh_i, bond, converged, sweeps, nrot_total);
 }
 
 #ifndef DQA_EMUL
@@ -1336,14 +1370,19 @@ __host__ __device__ inline size_t svd_cl_smem(int chi, int cs) {
   return sizeof(cplx) * (size_t)2 * gl * (2 * chi) + sizeof(double) * (4 * chi + 8) + sizeof(int) * (2 * chi + 8);
 }
 
-template <int RS, int CS, int MINB>  // CS CTAs per cluster (one SVD on CS SMs), MINB CTAs (of different SVDs) resident per SM
-__global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(RS * 32 / CS, MINB) k_jacobi_sys_cl(DqaDev d, int l, int mu, int p_step) {
+// CS CTAs per cluster (one SVD on CS SMs), MINB CTAs (of different SVDs) resident per SM, LPG lanes per group: a group
+// holds RS * LPG rows of its two columns.  Instantiated as <16, 2, 1, 8> for 56 < chi <= 64.  Measured and dropped: LPG = 16
+// (<8, 2, 1, 16>: twice the warps at half the rows per lane, one more shuffle stage) 1 386 vs 1 310 ms per step at chi = 64,
+// batch 296; four CTAs per SVD with two SVDs interleaved per SM (<16, 4, 2, 8>) 1 322 ms; two-CTA clusters at two per SM for
+// chi = 48 / 40 / 32 (<12|10|8, 2, 2|2|4, 8>) 504 vs 438, 363 vs 302, 507 vs 427 ms: below chi = 64 the one-CTA kernels win.
+template <int RS, int CS, int MINB, int LPG>
+__global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(RS * LPG * LPG / (2 * CS), MINB) k_jacobi_sys_cl(DqaDev d, int l, int mu, int p_step) {
   DQA_DYN_SMEM(smraw);
   cg::cluster_group cluster = cg::this_cluster();
   const int crank = (int)cluster.block_rank();
   const int inst = blockIdx.x / CS, tid = threadIdx.x, lane = tid & 31;
   const int chi = d.chi;
-  const int GL = (chi + CS - 1) / CS;  // groups per CTA (blockDim.x = 8 * GL rounded up to a warp)
+  const int GL = (chi + CS - 1) / CS;  // groups per CTA (blockDim.x = LPG * GL rounded up to a warp)
   cplx* lglob = d.lbuf + (size_t)inst * (size_t)(2 * chi) * (2 * chi);
   cplx* X = (cplx*)smraw;
   double* sig = (double*)(smraw + sizeof(cplx) * (size_t)2 * GL * (2 * chi));
@@ -1356,7 +1395,7 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(RS * 32 / CS, MINB)
   const int Q = qdim_prefix(qd1, d.N - l);
   const int k = mr < Q ? mr : Q;
   const int kp = k + (k & 1), h = kp >> 1;  // h groups hold the kp columns
-  const int gloc = tid >> 3, li = lane & 7;
+  const int gloc = tid / LPG, li = lane & (LPG - 1);
   const int g = crank * GL + gloc;           // position in the line of groups
   const bool act = gloc < GL && g < h;
   double* xn = ssorted;  // [2][GL] squared norms in flight
@@ -1364,7 +1403,7 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(RS * 32 / CS, MINB)
   cplx A[RS], B[RS];
 #pragma unroll
   for (int t = 0; t < RS; ++t) {
-    const int r = li + 8 * t;
+    const int r = li + LPG * t;
     const bool in = act && r < mr;
     B[t] = (in && 2 * g < k) ? lglob[r + (size_t)(2 * g) * (2 * chi)] : cmk(0.0, 0.0);
     A[t] = (in && 2 * g + 1 < k) ? lglob[r + (size_t)(2 * g + 1) * (2 * chi)] : cmk(0.0, 0.0);
@@ -1388,6 +1427,10 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(RS * 32 / CS, MINB)
       nA += cabs2(A[t]);
       nB += cabs2(B[t]);
     }
+    if (LPG == 16) {
+      nA += __shfl_xor_sync(DQA_FULL, nA, 8);
+      nB += __shfl_xor_sync(DQA_FULL, nB, 8);
+    }
     nA += __shfl_xor_sync(DQA_FULL, nA, 4);
     nB += __shfl_xor_sync(DQA_FULL, nB, 4);
     nA += __shfl_xor_sync(DQA_FULL, nA, 2);
@@ -1409,6 +1452,10 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(RS * 32 / CS, MINB)
         if (t + 1 < RS) g1 = cfmac(B[t + 1], A[t + 1], g1);
       }
       cplx gd = cadd(g0, g1);
+      if (LPG == 16) {
+        gd.x += __shfl_xor_sync(DQA_FULL, gd.x, 8);
+        gd.y += __shfl_xor_sync(DQA_FULL, gd.y, 8);
+      }
       gd.x += __shfl_xor_sync(DQA_FULL, gd.x, 4);
       gd.y += __shfl_xor_sync(DQA_FULL, gd.y, 4);
       gd.x += __shfl_xor_sync(DQA_FULL, gd.x, 2);
@@ -1464,7 +1511,7 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(RS * 32 / CS, MINB)
           cplx* dst = Xr + boff + (size_t)sr * mr;
 #pragma unroll
           for (int t = 0; t < RS; ++t)
-            if (li + 8 * t < mr) dst[li + 8 * t] = B[t];
+            if (li + LPG * t < mr) dst[li + LPG * t] = B[t];
           if (li == 0) xnr[noff + sr] = nB;
         }
         cluster.sync();
@@ -1472,7 +1519,7 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(RS * 32 / CS, MINB)
           const cplx* src = X + boff + (size_t)gloc * mr;
 #pragma unroll
           for (int t = 0; t < RS; ++t)
-            if (li + 8 * t < mr) B[t] = src[li + 8 * t];
+            if (li + LPG * t < mr) B[t] = src[li + LPG * t];
           nB = xn[noff + gloc];
         }
       } else {
@@ -1480,7 +1527,7 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(RS * 32 / CS, MINB)
           cplx* dst = Xl + boff + (size_t)sl * mr;
 #pragma unroll
           for (int t = 0; t < RS; ++t)
-            if (li + 8 * t < mr) dst[li + 8 * t] = A[t];
+            if (li + LPG * t < mr) dst[li + LPG * t] = A[t];
           if (li == 0) xnl[noff + sl] = nA;
         }
         cluster.sync();
@@ -1488,7 +1535,7 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(RS * 32 / CS, MINB)
           const cplx* src = X + boff + (size_t)gloc * mr;
 #pragma unroll
           for (int t = 0; t < RS; ++t)
-            if (li + 8 * t < mr) A[t] = src[li + 8 * t];
+            if (li + LPG * t < mr) A[t] = src[li + LPG * t];
           nA = xn[noff + gloc];
         }
       }
@@ -1512,7 +1559,7 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(RS * 32 / CS, MINB)
   if (act) {
 #pragma unroll
     for (int t = 0; t < RS; ++t) {
-      const int r = li + 8 * t;
+      const int r = li + LPG * t;
       if (r < mr) {
         lglob[r + (size_t)(2 * g) * (2 * chi)] = B[t];
         lglob[r + (size_t)(2 * g + 1) * (2 * chi)] = A[t];
@@ -1522,7 +1569,7 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(RS * 32 / CS, MINB)
   __threadfence();
   cluster.sync();
   if (crank != 0) return;  // no distributed-shared-memory access happens after the barrier above
-  jacobi_tail(d, inst, l, mu, p_step, lglob, 2 * chi, mr, k, kp, sig, ssorted, order, sh_i, bond, converged, sweeps, nrot_total);
+  jacobi_tail(jac_tail_args(d), inst, l, mu, p_step, lglob, 2 * chi, mr, k, kp, sig, ssorted, order, sh_i, bond, converged, sweeps, nrot_total);
 }
 #endif  // DQA_EMUL
 

@@ -483,3 +483,35 @@ def test_step_graph_replay_equals_plain_launches(monkeypatch):
         obj.run(print_info=False)
         res[mode] = obj.eps.copy()
     assert np.array_equal(res["1"], res["0"])
+
+
+def test_two_devices_in_one_process():
+    """A handle is bound to its own device: plans on cuda:0 and cuda:1 stepped alternately from one thread give the
+    single-device results, and the caller's current device is left alone (needs two GPUs; skipped otherwise)."""
+    import torch
+
+    from perceptron_dqa_b200._lib import Plan
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two CUDA devices")
+    g = golden("n7_chi4")
+    torch.cuda.set_device(0)
+    plans = []
+    for dev in (0, 1):
+        pl = Plan(g["xi"].shape[1], g["xi"].shape[0], int(g["P"]), float(g["dt"]), int(g["chi"]), batch=1, device=dev)
+        assert torch.cuda.current_device() == 0
+        pl.set_patterns(g["xi"][None])
+        pl.set_fourier(g["Uk_FT"], g["fxft"])
+        pl.reset_plus()
+        plans.append(pl)
+    for _ in range(3):
+        for pl in plans:
+            pl.step(1)
+            assert torch.cuda.current_device() == 0
+    a, b = plans[0].eps_trace()[0, :4], plans[1].eps_trace()[0, :4]
+    assert np.array_equal(a, b) and np.abs(a - g["eps"][:4]).max() < 1e-10
+    torch.cuda.set_device(1)
+    plans[0].step(1)  # launches on cuda:0 although cuda:1 is current
+    assert torch.cuda.current_device() == 1
+    assert abs(plans[0].eps_trace()[0, 4] - g["eps"][4]) < 1e-10
+    torch.cuda.set_device(0)

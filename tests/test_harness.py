@@ -55,3 +55,26 @@ def test_sweep_on_gpu(tmp_path):
     assert abs(c[3] - g["eps"][3]) < 1e-10
     vals = bm.run_batched([{"P": int(g["P"]), "dt": float(g["dt"]), "max_bond_dim": int(g["chi"]), "datafile": f}] * 2)
     assert vals[0] == vals[1] == v
+
+
+@pytest.mark.gpu
+def test_dt_grid_sweep_batched_on_gpu(tmp_path):
+    """benchmarker-mps.py:50-57 sweeps dt with one run per value; run_sweep_batched maps the grid onto the ensemble
+    dimension (one plan per (P, max_bond_dim, pattern shape)) and writes the same CSV rows in the same order."""
+    import numpy as np
+
+    from helpers import golden
+
+    g = golden("n7_chi4")
+    f = str(tmp_path / "patterns_5-7.npy")
+    np.save(f, g["xi"])
+    P, chi = int(g["P"]), int(g["chi"])
+    combos = [{"P": P, "dt": dt, "max_bond_dim": chi, "datafile": f} for dt in (0.3, float(g["dt"]), 1.1)]
+    combos.append({"P": P, "dt": 0.3, "max_bond_dim": chi + 2, "datafile": f})  # a second group (another bond dimension)
+    csv = str(tmp_path / "grid.csv")
+    vals = bm.run_sweep_batched(combos, csv, str(tmp_path / "errors.log"))
+    lines = open(csv).read().splitlines()
+    assert lines[0] == "P,dt,max_bond_dim,datafile,output" and len(lines) == 5
+    for s_, v, ln in zip(combos, vals, lines[1:]):
+        one = bm.function_to_run(**s_)
+        assert abs(v - one) < 1e-12 and ln.endswith(str(v))

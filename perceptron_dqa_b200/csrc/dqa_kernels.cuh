@@ -1181,7 +1181,7 @@ __global__ void __launch_bounds__(512) k_jacobi(DqaDev d, int l, int mu, int p_s
 #define JSYS_MINB8 2  // CTAs per SM the 8-row-slot systolic Jacobi is compiled for
 #endif
 template <int RS>
-__global__ void __launch_bounds__(RS * 32, RS > 8 ? 1 : (RS == 8 ? JSYS_MINB8 : (RS >= 6 ? 3 : (RS >= 4 ? 6 : 8)))) k_jacobi_sys(DqaDev d, int l, int mu, int p_step) {
+__device__ __forceinline__ void jacobi_sys_body(const DqaDev& d, int l, int mu, int p_step) {
   DQA_DYN_SMEM(smraw);
   const int inst = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
   const int chi = d.chi;
@@ -1352,6 +1352,14 @@ __global__ void __launch_bounds__(RS * 32, RS > 8 ? 1 : (RS == 8 ? JSYS_MINB8 : 
   __syncthreads();
   jacobi_tail(jac_tail_args(d), inst, l, mu, p_step, X, mr, mr, k, kp, sig, ssorted, order, sh_i, bond, converged, sweeps, nrot_total);
 }
+
+template <int RS>
+__global__ void __launch_bounds__(RS * 32, RS > 8 ? 1 : (RS == 8 ? JSYS_MINB8 : (RS >= 6 ? 3 : (RS >= 4 ? 6 : 8)))) k_jacobi_sys(DqaDev d, int l, int mu, int p_step) {
+  jacobi_sys_body<RS>(d, l, mu, p_step);
+}
+// (A 14-row-slot build for 48 < chi <= 56 does not exist: 448 threads are 14 warps, four on two of the SM's sub-partitions, and a
+// sub-partition's 16 K registers hold four warps only up to 128 registers per thread -- 112 of which the column data would take.
+// It spills at 128 (1 142 vs 982 ms per step for the shared-memory kernel at chi = 56) and cannot launch at 144.)
 
 #ifndef DQA_EMUL
 // ---------------------------------------------------------------------------------

@@ -111,8 +111,74 @@ def test_bond_64_kernels(factory):
 
 
 def test_bond_48_saturated(factory):
-    # 32 < chi <= 56 at saturation: k_sector_qr<12>, blocked LQ with 96 rows, the shared-memory-resident k_jacobi
+    # chi = 48 at saturation: k_sector_qr<12>, blocked LQ with 96 rows, the 12-row-slot systolic Jacobi (one CTA per SM on the GPU)
     ps.check_teacher_forced(factory, "n12_chi48_saturated")
+
+
+def test_round2_abi_on_the_emulator():
+    """The round-2 entry points through the same C ABI on the CPU build: truncation-policy plan fields and the discarded-weight
+    trace against the numpy sector model, per-instance dt tables against single-dt plans, status words cleared by a new state."""
+    import numpy as np
+
+    import dqa_oracle as O
+    import emul_lib
+    import sector_model as S
+    from helpers import golden, snapshots
+    from perceptron_dqa_b200._lib import DqaError, Plan
+
+    lib = emul_lib.load()
+    kw = dict(lib=lib, workspace=emul_lib.numpy_workspace)
+    g = golden("n7_chi4")
+    xi, P, dt, chi = g["xi"], int(g["P"]), float(g["dt"]), int(g["chi"])
+    n, nx = xi.shape[1], xi.shape[0]
+    hbit, _, _ = O.hamming_tables(xi)
+    p, mu, pre, _post = snapshots(g)[2]
+    u = S.uz_diagonal(g["Uk_FT"][:, p], n)
+    nbit = np.stack([hbit[mu], 1 - hbit[mu]], axis=1)
+    for mode, renorm, cutoff in ((4, 0, 1e-10), (2, 0, 5e-2), (5, 1, 1e-2)):
+        pl = Plan(n, nx, P, dt, chi, cutoff=cutoff, cutoff_mode=mode, renorm=renorm, absorb=1, **kw)
+        pl.set_patterns(xi[None])
+        pl.set_fourier(g["Uk_FT"], g["fxft"])
+        pl.set_mps(pre)
+        pl.apply_pattern(p, mu)
+        got = pl.get_mps()
+        stats = []
+        want = S.apply_pattern_sector([t.copy() for t in pre], u, nbit, chi, cutoff=cutoff, cutoff_mode=mode, renorm=renorm, stats=stats)
+        assert [t.shape for t in got] == [t.shape for t in want]
+        assert abs(abs(O.overlap(got, want)) / np.sqrt(O.mps_norm2(got) * O.mps_norm2(want)) - 1.0) < 1e-12
+        w = pl.truncation_error()
+        for l, _shape, sv, n_chi in stats:
+            assert abs(w[l] - float((sv[n_chi:] ** 2).sum()) / float((sv ** 2).sum())) < 1e-13
+    with pytest.raises(DqaError):
+        Plan(n, nx, P, dt, chi, cutoff_mode=4, renorm=2, absorb=-1, **kw)
+    # two instances with different dt in one plan == two single-dt plans
+    dts = [dt, 0.4]
+    uks = np.stack([O.fourier_tables(n, P, v)[0] for v in dts])
+    both = Plan(n, nx, P, dt, chi, batch=2, n_tables=2, **kw)
+    both.set_patterns(np.stack([xi, xi]))
+    both.set_fourier_tables(uks, g["fxft"], [0, 1], dts)
+    both.reset_plus()
+    both.step(2)
+    for i, v in enumerate(dts):
+        one = Plan(n, nx, P, v, chi, **kw)
+        one.set_patterns(xi[None])
+        one.set_fourier(uks[i], g["fxft"])
+        one.reset_plus()
+        one.step(2)
+        assert np.abs(both.eps_trace()[i, :3] - one.eps_trace()[0, :3]).max() < 1e-13
+    assert np.abs(both.eps_trace()[0, :3] - g["eps"][:3]).max() < 1e-10
+    with pytest.raises(DqaError):
+        both.set_fourier(uks[0], g["fxft"])  # a two-table plan wants set_fourier_tables
+    # a non-finite state raises and sets the status word; loading a state clears it
+    good = both.get_mps(0)
+    bad = [t.copy() for t in good]
+    bad[2][...] = np.nan
+    both.set_mps(bad, 0)
+    with pytest.raises(DqaError):
+        both.step(1)
+    assert both.status()[0] != 0 and both.status()[1] == 0
+    both.set_mps(good, 0)
+    assert both.status()[0] == 0
 
 
 @pytest.mark.parametrize("seed", [1, 2])

@@ -30,6 +30,8 @@ static void (*const KJ_Y3)(DqaDev, int, int, int) = k_jacobi_sys<3>;
 static void (*const KJ_Y4)(DqaDev, int, int, int) = k_jacobi_sys<4>;
 static void (*const KJ_Y6)(DqaDev, int, int, int) = k_jacobi_sys<6>;
 static void (*const KJ_Y8)(DqaDev, int, int, int) = k_jacobi_sys<8>;
+static void (*const KJ_B1)(DqaDev, int, int, int) = k_jacobi_blk<1>;  // row-per-lane block ordering: 2chi <= 32 rows
+static void (*const KJ_B2)(DqaDev, int, int, int) = k_jacobi_blk<2>;  // 2chi <= 64 rows
 static void (*const KJ_Y10)(DqaDev, int, int, int) = k_jacobi_sys<10>;  // chi <= 40 .. 64: one CTA per SM, the factor still in registers
 static void (*const KJ_Y12)(DqaDev, int, int, int) = k_jacobi_sys<12>;
 #ifndef DQA_EMUL
@@ -54,6 +56,8 @@ struct dqa_handle {
   bool use_graph = false, capturing = false;
   long long graph_nodes = 0;
   bool jac_sys;
+  int jac_blk = 0;  // DQA_JAC_BLK: 1 = k_jacobi_blk for chi <= 32
+  size_t jac_pad = 0;  // DQA_JAC_SMEM_PAD: extra dynamic shared memory of the systolic Jacobi (occupancy experiments: >= 50 KB leaves one CTA per SM at chi = 32)
   int jac_sys_big = 2;  // systolic Jacobi above chi = 32 (DQA_JAC_SYS_BIG): 0 off; 1: chi <= 48 (one CTA per SM, 166 registers); 2: also 56 < chi <= 64 on a cluster of two CTAs
   char err[512];
   // profiling
@@ -269,6 +273,10 @@ extern "C" int dqa_create(dqa_t** out, const dqa_config* cfg) {
     env = getenv("DQA_JAC_SYS_BIG");
     if (env) h->jac_sys_big = atoi(env);
     if (!h->jac_sys) h->jac_sys_big = 0;
+    env = getenv("DQA_JAC_BLK");
+    if (env) h->jac_blk = atoi(env);
+    env = getenv("DQA_JAC_SMEM_PAD");
+    if (env && atol(env) > 0) h->jac_pad = (size_t)atol(env);
   }
   DevGuard guard(c.device);
   {
@@ -285,7 +293,7 @@ extern "C" int dqa_create(dqa_t** out, const dqa_config* cfg) {
   DQA_OPTIN(k_sector_qr<8>); DQA_OPTIN(k_sector_qr<10>); DQA_OPTIN(k_sector_qr<12>); DQA_OPTIN(k_sector_qr<16>);
   DQA_OPTIN(KJ_0S); DQA_OPTIN(KJ_0G);
   DQA_OPTIN(KJ_Y2); DQA_OPTIN(KJ_Y3); DQA_OPTIN(KJ_Y4); DQA_OPTIN(KJ_Y6); DQA_OPTIN(KJ_Y8);
-  DQA_OPTIN(KJ_Y10); DQA_OPTIN(KJ_Y12);
+  DQA_OPTIN(KJ_Y10); DQA_OPTIN(KJ_Y12); DQA_OPTIN(KJ_B1); DQA_OPTIN(KJ_B2);
 #ifndef DQA_EMUL
   DQA_OPTIN(KJ_C16);
 #endif
@@ -531,11 +539,13 @@ static int launch_truncate(dqa_t* h, int p, int mu) {
     {
       // chi <= 32: the systolic kernel (2chi <= 8 RS rows per column); above: L in shared memory (chi <= 56) or in L2
       const int t_sys = 32 * ((d.chi + 3) / 4);  // one 8-lane group per column pair
-      if (h->jac_sys && d.chi <= 8) HL(KJ_Y2, dim3(d.batch), dim3(t_sys), svd_smem(d.chi), h->stream, d, l, mu, p);
+      if (h->jac_blk && d.chi <= 16) HL(KJ_B1, dim3(d.batch), dim3(t_sys), svd_blk_smem(d.chi), h->stream, d, l, mu, p);
+      else if (h->jac_blk && d.chi <= 32) HL(KJ_B2, dim3(d.batch), dim3(t_sys), svd_blk_smem(d.chi) + h->jac_pad, h->stream, d, l, mu, p);
+      else if (h->jac_sys && d.chi <= 8) HL(KJ_Y2, dim3(d.batch), dim3(t_sys), svd_smem(d.chi), h->stream, d, l, mu, p);
       else if (h->jac_sys && d.chi <= 12) HL(KJ_Y3, dim3(d.batch), dim3(t_sys), svd_smem(d.chi), h->stream, d, l, mu, p);
       else if (h->jac_sys && d.chi <= 16) HL(KJ_Y4, dim3(d.batch), dim3(t_sys), svd_smem(d.chi), h->stream, d, l, mu, p);
       else if (h->jac_sys && d.chi <= 24) HL(KJ_Y6, dim3(d.batch), dim3(t_sys), svd_smem(d.chi), h->stream, d, l, mu, p);
-      else if (h->jac_sys && d.chi <= 32) HL(KJ_Y8, dim3(d.batch), dim3(t_sys), svd_smem(d.chi), h->stream, d, l, mu, p);
+      else if (h->jac_sys && d.chi <= 32) HL(KJ_Y8, dim3(d.batch), dim3(t_sys), svd_smem(d.chi) + h->jac_pad, h->stream, d, l, mu, p);
       else if (h->jac_sys_big && d.chi <= 40) HL(KJ_Y10, dim3(d.batch), dim3(t_sys), svd_smem(d.chi), h->stream, d, l, mu, p);
       else if (h->jac_sys_big && d.chi <= 48) HL(KJ_Y12, dim3(d.batch), dim3(t_sys), svd_smem(d.chi), h->stream, d, l, mu, p);
 #ifndef DQA_EMUL

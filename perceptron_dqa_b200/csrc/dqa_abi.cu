@@ -30,8 +30,6 @@ static void (*const KJ_Y3)(DqaDev, int, int, int) = k_jacobi_sys<3>;
 static void (*const KJ_Y4)(DqaDev, int, int, int) = k_jacobi_sys<4>;
 static void (*const KJ_Y6)(DqaDev, int, int, int) = k_jacobi_sys<6>;
 static void (*const KJ_Y8)(DqaDev, int, int, int) = k_jacobi_sys<8>;
-static void (*const KJ_B1)(DqaDev, int, int, int) = k_jacobi_blk<1>;  // row-per-lane block ordering: 2chi <= 32 rows
-static void (*const KJ_B2)(DqaDev, int, int, int) = k_jacobi_blk<2>;  // 2chi <= 64 rows
 static void (*const KJ_Y10)(DqaDev, int, int, int) = k_jacobi_sys<10>;  // chi <= 40 .. 64: one CTA per SM, the factor still in registers
 static void (*const KJ_Y12)(DqaDev, int, int, int) = k_jacobi_sys<12>;
 #ifndef DQA_EMUL
@@ -54,9 +52,15 @@ struct dqa_handle {
   cudaStream_t cap_stream = nullptr;   // capture stream of the step graph (the handle's own stream may be the legacy one)
   cudaGraphExec_t step_graph = nullptr;  // one dQA step with the step counter read from the device
   bool use_graph = false, capturing = false;
+  // the captured step runs the batch as n_split independent sub-batches on parallel branches of the graph (DQA_SPLIT): every
+  // launch of the step ends in a tail where the last CTAs of the batch finish on otherwise idle SMs; the branches fill
+  // each other's tails (measured at batch 888: +3.3 % realisation-steps/s with two branches, +4.0 % with three, +3.7 % with four
+  // at chi = 32; +4.6 % with three at chi = 10 and 20; +3 % with two at batch 148 and 296; +-0 at batch 128)
+  int n_split = 1;
+  cudaStream_t split_stream[3] = {nullptr, nullptr, nullptr};
+  cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
   long long graph_nodes = 0;
   bool jac_sys;
-  int jac_blk = 0;  // DQA_JAC_BLK: 1 = k_jacobi_blk for chi <= 32
   size_t jac_pad = 0;  // DQA_JAC_SMEM_PAD: extra dynamic shared memory of the systolic Jacobi (occupancy experiments: >= 50 KB leaves one CTA per SM at chi = 32)
   int jac_sys_big = 2;  // systolic Jacobi above chi = 32 (DQA_JAC_SYS_BIG): 0 off; 1: chi <= 48 (one CTA per SM, 166 registers); 2: also 56 < chi <= 64 on a cluster of two CTAs
   char err[512];
@@ -149,6 +153,35 @@ static void carve(const dqa_config& c, DqaDev& d, Aux& aux, char* base, size_t* 
   aux.d_e = cv.take<int32_t>(nx * N * 2);
   aux.d_q = cv.take<int32_t>(nx * N * 2 * D);
   *total = cv.off;
+}
+
+// The plan restricted to instances [i0, i0 + nb): every per-instance buffer advanced by i0 strides (same table as carve()).
+static DqaDev view_of(const DqaDev& f, const dqa_config& c, size_t i0, int nb) {
+  DqaDev d = f;
+  const size_t N = c.N, chi = c.chi, P = c.P, nx = c.n_xi;
+  d.batch = nb;
+  d.mps += i0 * N * 2 * chi * chi;
+  d.bond += i0 * (N + 1);
+  d.hbit += i0 * nx * N;
+  d.tab += i0;
+  d.dtv += i0;
+  d.rbuf += i0 * 2 * f.smax * chi * chi;
+  d.qbuf += i0 * (size_t)f.nsec_total * 2 * chi * chi;
+  d.qdim += i0 * (N + 1) * f.smax;
+  d.theta += i0 * 2 * 2 * chi * (size_t)f.ld_theta;
+  d.work += i0 * 2 * chi * (size_t)f.ld_theta;
+  d.lbuf += i0 * 4 * chi * chi;
+  d.scale += i0;
+  d.schmidt += i0 * N * 2 * chi;
+  d.nsv += i0 * N;
+  d.tmk += i0 * nx * f.kh;
+  d.eps += i0 * (P + 1);
+  d.escratch += i0;
+  d.discw += i0 * N;
+  d.bdmon += i0 * P * nx;
+  d.status += i0;
+  d.counters += i0 * DQA_NCNT;
+  return d;
 }
 
 extern "C" const char* dqa_version(void) { return "dqa-b200 0.1 (sector path, complex128)"; }
@@ -266,6 +299,11 @@ extern "C" int dqa_create(dqa_t** out, const dqa_config* cfg) {
 #ifdef DQA_EMUL
     h->use_graph = false;
 #endif
+    env = getenv("DQA_SPLIT");  // sub-batches on parallel graph branches (measured, N=21: never slower; nothing to gain below a wave)
+    h->n_split = env ? atoi(env) : (c.batch >= 444 ? 3 : (c.batch >= 148 ? 2 : 1));
+    if (h->n_split < 1) h->n_split = 1;
+    if (h->n_split > 4) h->n_split = 4;
+    if (h->n_split > c.batch) h->n_split = c.batch;
   }
   {
     const char* env = getenv("DQA_JAC_SYS");  // 0: use the shared-memory-resident Jacobi for every chi
@@ -273,8 +311,6 @@ extern "C" int dqa_create(dqa_t** out, const dqa_config* cfg) {
     env = getenv("DQA_JAC_SYS_BIG");
     if (env) h->jac_sys_big = atoi(env);
     if (!h->jac_sys) h->jac_sys_big = 0;
-    env = getenv("DQA_JAC_BLK");
-    if (env) h->jac_blk = atoi(env);
     env = getenv("DQA_JAC_SMEM_PAD");
     if (env && atol(env) > 0) h->jac_pad = (size_t)atol(env);
   }
@@ -293,7 +329,7 @@ extern "C" int dqa_create(dqa_t** out, const dqa_config* cfg) {
   DQA_OPTIN(k_sector_qr<8>); DQA_OPTIN(k_sector_qr<10>); DQA_OPTIN(k_sector_qr<12>); DQA_OPTIN(k_sector_qr<16>);
   DQA_OPTIN(KJ_0S); DQA_OPTIN(KJ_0G);
   DQA_OPTIN(KJ_Y2); DQA_OPTIN(KJ_Y3); DQA_OPTIN(KJ_Y4); DQA_OPTIN(KJ_Y6); DQA_OPTIN(KJ_Y8);
-  DQA_OPTIN(KJ_Y10); DQA_OPTIN(KJ_Y12); DQA_OPTIN(KJ_B1); DQA_OPTIN(KJ_B2);
+  DQA_OPTIN(KJ_Y10); DQA_OPTIN(KJ_Y12);
 #ifndef DQA_EMUL
   DQA_OPTIN(KJ_C16);
 #endif
@@ -313,6 +349,11 @@ extern "C" void dqa_destroy(dqa_t* h) {
   if (h->step_graph) cudaGraphExecDestroy(h->step_graph);
   if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
 #endif
+  for (int i = 0; i < 3; ++i) {
+    if (h->split_stream[i]) cudaStreamDestroy(h->split_stream[i]);
+    if (h->ev_join[i]) cudaEventDestroy(h->ev_join[i]);
+  }
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   delete h;
 }
 
@@ -539,9 +580,7 @@ static int launch_truncate(dqa_t* h, int p, int mu) {
     {
       // chi <= 32: the systolic kernel (2chi <= 8 RS rows per column); above: L in shared memory (chi <= 56) or in L2
       const int t_sys = 32 * ((d.chi + 3) / 4);  // one 8-lane group per column pair
-      if (h->jac_blk && d.chi <= 16) HL(KJ_B1, dim3(d.batch), dim3(t_sys), svd_blk_smem(d.chi), h->stream, d, l, mu, p);
-      else if (h->jac_blk && d.chi <= 32) HL(KJ_B2, dim3(d.batch), dim3(t_sys), svd_blk_smem(d.chi) + h->jac_pad, h->stream, d, l, mu, p);
-      else if (h->jac_sys && d.chi <= 8) HL(KJ_Y2, dim3(d.batch), dim3(t_sys), svd_smem(d.chi), h->stream, d, l, mu, p);
+      if (h->jac_sys && d.chi <= 8) HL(KJ_Y2, dim3(d.batch), dim3(t_sys), svd_smem(d.chi), h->stream, d, l, mu, p);
       else if (h->jac_sys && d.chi <= 12) HL(KJ_Y3, dim3(d.batch), dim3(t_sys), svd_smem(d.chi), h->stream, d, l, mu, p);
       else if (h->jac_sys && d.chi <= 16) HL(KJ_Y4, dim3(d.batch), dim3(t_sys), svd_smem(d.chi), h->stream, d, l, mu, p);
       else if (h->jac_sys && d.chi <= 24) HL(KJ_Y6, dim3(d.batch), dim3(t_sys), svd_smem(d.chi), h->stream, d, l, mu, p);
@@ -646,6 +685,64 @@ static int step_impl(dqa_t* h, int nsteps, bool check);
 extern "C" int dqa_step(dqa_t* h, int nsteps) { return step_impl(h, nsteps, true); }
 // same launches, no host synchronisation and no status check: lets several handles on different streams overlap
 extern "C" int dqa_step_async(dqa_t* h, int nsteps) { return step_impl(h, nsteps, false); }
+// One whole step (n_xi pattern sub-steps, mixer, energy) on h->stream.  p >= 0: step index known on the host; p < 0: the
+// graph form, every kernel reads the step index from device memory.  With n_split > 1 the batch runs as n_split independent
+// sub-batches: branch 0 on h->stream, the others on the handle's own streams, forked and joined with events -- inside a
+// stream capture this makes parallel branches of the graph.  Profiling runs keep one branch (per-family event timers).
+static int launch_step(dqa_t* h, int p) {
+  const int ns = h->profiling ? 1 : h->n_split;
+  const DqaDev full = h->dev;
+  cudaStream_t main_stream = h->stream;
+  struct Restore {
+    dqa_t* h;
+    const DqaDev& full;
+    cudaStream_t st;
+    ~Restore() {
+      h->dev = full;
+      h->stream = st;
+    }
+  } restore_{h, full, main_stream};
+  if (ns > 1) {
+    if (!h->ev_fork) CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+    for (int s = 1; s < ns; ++s) {
+      if (!h->split_stream[s - 1]) CK(cudaStreamCreateWithFlags(&h->split_stream[s - 1], cudaStreamNonBlocking));
+      if (!h->ev_join[s - 1]) CK(cudaEventCreateWithFlags(&h->ev_join[s - 1], cudaEventDisableTiming));
+    }
+    CK(cudaEventRecord(h->ev_fork, main_stream));
+  }
+  for (int s = 0; s < ns; ++s) {
+    if (ns > 1) {
+      const size_t i0 = (size_t)full.batch * s / ns, i1 = (size_t)full.batch * (s + 1) / ns;
+      h->dev = view_of(full, h->cfg, i0, (int)(i1 - i0));
+      if (s > 0) {
+        h->stream = h->split_stream[s - 1];
+        CK(cudaStreamWaitEvent(h->stream, h->ev_fork, 0));
+      }
+    }
+    for (int mu = 0; mu < h->cfg.n_xi; ++mu) {
+      int rc = launch_canonize(h, mu);
+      if (rc) return rc;
+      rc = launch_truncate(h, p < 0 ? -1 : p, mu);
+      if (rc) return rc;
+    }
+    int rc;
+    if (p < 0) {
+      rc = launch_mixer(h, 0.0, 0.0, 2);
+    } else {
+      const double s_p = (double)(p + 1) / h->cfg.P;
+      const double beta = (1.0 - s_p) * h->cfg.dt;  // dQA_mps.py:88-89
+      rc = launch_mixer(h, beta, 1.0 - s_p, full.ntab > 1 ? 1 : 0);  // several tables: beta = (1 - s_p) * dt of each instance
+    }
+    if (rc) return rc;
+    rc = launch_energy(h, p < 0 ? -2 : p + 1);
+    if (rc) return rc;
+    if (s > 0) CK(cudaEventRecord(h->ev_join[s - 1], h->stream));
+    h->stream = main_stream;
+  }
+  for (int s = 1; s < ns; ++s) CK(cudaStreamWaitEvent(main_stream, h->ev_join[s - 1], 0));
+  return DQA_OK;
+}
+
 // One dQA step captured as a CUDA graph: the launch grid depends only on (N, n_xi, chi, batch), never on data, and every
 // kernel that needs the step index reads it from device memory (p < 0), so the same executable graph replays for every
 // step.  Pays off when the kernels are short (a single realisation, small bonds): 1 431 launches per step at N=21.
@@ -658,12 +755,7 @@ static int build_step_graph(dqa_t* h) {
   cudaError_t e = cudaStreamBeginCapture(h->cap_stream, cudaStreamCaptureModeThreadLocal);
   int rc = DQA_OK;
   if (e == cudaSuccess) {
-    for (int mu = 0; mu < h->cfg.n_xi && rc == DQA_OK; ++mu) {
-      rc = launch_canonize(h, mu);
-      if (rc == DQA_OK) rc = launch_truncate(h, -1, mu);
-    }
-    if (rc == DQA_OK) rc = launch_mixer(h, 0.0, 0.0, 2);
-    if (rc == DQA_OK) rc = launch_energy(h, -2);
+    rc = launch_step(h, -1);
     if (rc == DQA_OK) HL(k_advance, dim3(1), dim3(32), 0, h->stream, h->dev);
     cudaGraph_t g = nullptr;
     e = cudaStreamEndCapture(h->cap_stream, &g);
@@ -699,18 +791,7 @@ static int step_impl(dqa_t* h, int nsteps, bool check) {
     }
   }
   for (int it = 0; it < nsteps; ++it) {
-    const int p = h->pp;
-    const double s_p = (double)(p + 1) / h->cfg.P;
-    const double beta = (1.0 - s_p) * h->cfg.dt;  // dQA_mps.py:88-89
-    for (int mu = 0; mu < h->cfg.n_xi; ++mu) {
-      int rc = launch_canonize(h, mu);
-      if (rc) return rc;
-      rc = launch_truncate(h, p, mu);
-      if (rc) return rc;
-    }
-    int rc = launch_mixer(h, beta, 1.0 - s_p, h->dev.ntab > 1 ? 1 : 0);  // several tables: beta = (1 - s_p) * dt of each instance
-    if (rc) return rc;
-    rc = launch_energy(h, p + 1);
+    const int rc = launch_step(h, h->pp);
     if (rc) return rc;
     h->pp++;
   }

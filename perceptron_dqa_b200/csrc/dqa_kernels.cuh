@@ -1362,364 +1362,18 @@ __global__ void __launch_bounds__(RS * 32, RS > 8 ? 1 : (RS == 8 ? JSYS_MINB8 : 
 // It spills at 128 (1 142 vs 982 ms per step for the shared-memory kernel at chi = 56) and cannot launch at 144.)
 
 
-// ---------------------------------------------------------------------------------
-// k_jacobi_blk: the same SVD + trim as k_jacobi_sys with the columns laid out ROW-PER-LANE, so that three of four
-// rotation rounds need neither shared memory nor a block barrier.
-// A warp owns 8 columns for a whole block-round, as two half-blocks A[0..3], B[0..3]; lane j holds rows j, j+32, ...
-// (RL rows per lane and column).  A rotation of two columns of the warp is then lane-local (no shuffle, no shared
-// memory); only the dot products are warp-wide sums.  One sub-round = the 4 disjoint pairs (A_i, B_(i+j)%4): the 4
-// complex partial dots are summed by a reduce-scatter butterfly (12 double shuffles instead of 40) that leaves pair k's
-// sum in lanes 8k..8k+7, which compute the rotation parameters of the 4 pairs SIMT-parallel (the scalar chain is paid
-// once per sub-round) and publish (c, z) through 32 bytes of warp-private shared memory (__syncwarp only).  After the 4
-// sub-rounds of a block-round all 16 cross pairs of the two half-blocks have met, and ONE half-block crosses shared
-// memory to the neighbouring warp behind ONE block barrier: the odd-even transposition ordering of k_jacobi_sys with
-// half-blocks as items and warps as groups (2*warps block-rounds per sweep).  The 6 pairs inside every half-block are
-// taken at the start of the sweep (3 sub-rounds).  Per sweep: 8*warps + 3 sub-rounds, 2*warps barriers (k_jacobi_sys:
-// 8*warps rounds and as many barriers).  On the L factors of a chi=32 run this ordering needs 13 % fewer sweeps than the
-// column-wise odd-even one (tools/jacobi_study.py).  Squared norms: group k keeps |A_k|^2 and the norm of its current
-// partner, which hops one group per sub-round; exact norms once per sweep.
-// shared: exchange buffers 2 x (warps x 4 x mr), reused for the final columns | sig | xn/ssorted | order | sh_i | pb
-// ---------------------------------------------------------------------------------
-__host__ __device__ inline int svd_blk_cols(int chi) { return 8 * ((2 * chi + 7) / 8); }
-__host__ __device__ inline int svd_blk_rows(int chi) { return 32 * ((2 * chi + 31) / 32); }  // rows padded to whole lanes: static strides
-__host__ __device__ inline size_t svd_blk_smem(int chi) {
-  const size_t kcm = (size_t)svd_blk_cols(chi);
-  return sizeof(cplx) * (size_t)svd_blk_rows(chi) * kcm + sizeof(double) * (2 * kcm + 8) + sizeof(int) * (kcm + 8) + sizeof(double) * 32 * (kcm / 8) + 64;
-}
 
-// v[k][0..NV) summed over the warp; on return lanes 8k..8k+7 hold the totals of slot k in out[0..NV)
-template <int NV>
-__device__ __forceinline__ void warp_reduce_scatter4(const double (&v)[4][NV], double (&out)[NV], int lane) {
-  const bool h4 = lane & 16, h3 = lane & 8;
-  double a[2][NV];
-#pragma unroll
-  for (int s = 0; s < 2; ++s)
-#pragma unroll
-    for (int e = 0; e < NV; ++e) {
-      const double send = h4 ? v[s][e] : v[s + 2][e];
-      const double keep = h4 ? v[s + 2][e] : v[s][e];
-      a[s][e] = keep + __shfl_xor_sync(DQA_FULL, send, 16);
-    }
-#pragma unroll
-  for (int e = 0; e < NV; ++e) {
-    const double send = h3 ? a[0][e] : a[1][e];
-    const double keep = h3 ? a[1][e] : a[0][e];
-    out[e] = keep + __shfl_xor_sync(DQA_FULL, send, 8);
-  }
-#pragma unroll
-  for (int o = 4; o > 0; o >>= 1)
-#pragma unroll
-    for (int e = 0; e < NV; ++e) out[e] += __shfl_xor_sync(DQA_FULL, out[e], o);
-}
-
-// rotation parameters of k_jacobi_sys (no division): returns 1 if the pair rotates; A' = c A + z B, B' = c B - conj(z) A
-__device__ __forceinline__ int jac_params(cplx gd, double& nA, double& nB, double tol2, double quad2, double& c, cplx& z, int& big) {
-  const double ag2 = cabs2(gd);
-  if (!(ag2 > tol2 * nA * nB && ag2 > 0.0)) return 0;
-  const double dl = 0.5 * (nB - nA), ad = fabs(dl);
-  const double r2 = fma(dl, dl, ag2);
-  const double r = r2 * rsqrt(r2);
-  const double u = r + ad;
-  const double q = rsqrt(2.0 * r * u);
-  c = u * q;
-  const double sq = copysign(q, dl);
-  z = cmk(-sq * gd.x, sq * gd.y);  // -s e^{-i phi}
-  const double tg = copysign(2.0 * ag2 * r * q * q, dl);
-  if (ag2 > quad2 * nA * nB) big = 1;
-  nA -= tg;
-  nB += tg;
-  nA = nA > 0.0 ? nA : 0.0;
-  nB = nB > 0.0 ? nB : 0.0;
-  return 1;
-}
-
-template <int RL>
-__device__ __forceinline__ void jac_rot(cplx (&P)[RL], cplx (&Q)[RL], double c, cplx z) {
-  const cplx z2 = cmk(-z.x, z.y);
-#pragma unroll
-  for (int t = 0; t < RL; ++t) {
-    const cplx a_ = P[t], b_ = Q[t];
-    P[t] = cfma(z, b_, cscale(a_, c));
-    Q[t] = cfma(z2, a_, cscale(b_, c));
-  }
-}
-
-template <int RL>
-__device__ __forceinline__ void jacobi_blk_body(const DqaDev& d, int l, int mu, int p_step) {
-  DQA_DYN_SMEM(smraw);
-  const int inst = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-  const int chi = d.chi, kcm = svd_blk_cols(chi);
-  const cplx* lglob = d.lbuf + (size_t)inst * (size_t)(2 * chi) * (2 * chi);
-  cplx* X = (cplx*)smraw;
-  constexpr int MRC = 32 * RL;  // row stride of the exchange slots and of the parked columns (compile-time: immediates)
-  double* sig = (double*)(smraw + sizeof(cplx) * (size_t)svd_blk_rows(chi) * kcm);
-  double* ssorted = sig + kcm;
-  int* order = (int*)(ssorted + kcm + 8);
-  int* sh_i = order + kcm;  // [0]=rotation count, [1]=n_chi, [2]=some rotated pair was above the quadratic threshold
-  double* pb = (double*)(((uintptr_t)(sh_i + 8) + 15) & ~(uintptr_t)15) + (size_t)w * 32;  // [2][4 pairs][4]: c, z.x, z.y
-  int* bond = d.bond + inst * (d.N + 1);
-  const int mr = 2 * bond[l];
-  const int* qd1 = d.qdim + ((size_t)inst * (d.N + 1) + (l + 1)) * d.smax;
-  const int Q = qdim_prefix(qd1, d.N - l);
-  const int k = mr < Q ? mr : Q;
-  const int h = (k + 7) >> 3, kc = 8 * h;  // h warps hold the kc columns (zero columns pad the last warp)
-  const bool act = w < h;
-  const bool h4 = lane & 16, h3 = lane & 8;
-  const int kk = lane >> 3, li = lane & 7;  // this lane computes the parameters of pair kk of the sub-round
-  double* xn = ssorted;                     // [2][4h] squared norms in flight (ssorted is only used by the tail)
-
-  cplx A[4][RL], B[4][RL];
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int t = 0; t < RL; ++t) {
-      const int r = lane + 32 * t, ca = 8 * w + i, cb = ca + 4;
-      const bool in = act && r < mr;
-      A[i][t] = (in && ca < k) ? lglob[r + (size_t)ca * (2 * chi)] : cmk(0.0, 0.0);
-      B[i][t] = (in && cb < k) ? lglob[r + (size_t)cb * (2 * chi)] : cmk(0.0, 0.0);
-    }
-  const int gr = (w + 1 < h) ? w + 1 : 0, gl = (w > 0) ? w - 1 : h - 1;  // ring neighbours (only the parked half-block wraps)
-  const size_t bufsz = (size_t)h * 4 * MRC;
-  const double tol = sqrt((double)mr) * 2.220446049250313e-16, tol2 = tol * tol;
-  const double quad2 = d.jac_quad2;
-  int sweeps = 0, converged = (k <= 1);
-  unsigned long long nrot_total = 0;
-  int pbsel = 0;
-
-// one sub-round: pairs (P_k, Q_k), k = 0..3, given as macro arguments so that every register index is static
-#define JB_DOT(P, Q, acc)                                \
-  {                                                      \
-    cplx g_ = cmk(0.0, 0.0);                             \
-    _Pragma("unroll") for (int t = 0; t < RL; ++t) g_ = cfmac(Q[t], P[t], g_); \
-    acc[0] = g_.x;                                       \
-    acc[1] = g_.y;                                       \
-  }
-#define JB_APPLY(idx, P, Q)                                                   \
-  if ((fired >> (8 * idx)) & 1u) {                                            \
-    const double2 cz = *reinterpret_cast<const double2*>(pbw + 4 * idx);      \
-    const double zy = pbw[4 * idx + 2];                                       \
-    jac_rot<RL>(P, Q, cz.x, cmk(cz.y, zy));                                   \
-  }
-#define JB_PUBLISH()                                                          \
-  double* pbw = pb + 16 * pbsel;                                              \
-  pbsel ^= 1;                                                                 \
-  if (rot && li == 0) {                                                       \
-    *reinterpret_cast<double2*>(pbw + 4 * kk) = make_double2(c_, z_.x);       \
-    pbw[4 * kk + 2] = z_.y;                                                   \
-    myrot++;                                                                  \
-  }                                                                           \
-  __syncwarp();                                                               \
-  const unsigned fired = __ballot_sync(DQA_FULL, rot);
-// cross pairs (A_i, B_(i+J)%4); group kk owns |A_kk|^2 (nA) and the norm of its current partner (nB)
-#define JB_RS2(D0, D1, D2, D3, out)                                           \
-  {                                                                           \
-    double a0_[2], a1_[2];                                                    \
-    {                                                                         \
-      double p_[2], q_[2];                                                    \
-      D0(p_);                                                                 \
-      D2(q_);                                                                 \
-      _Pragma("unroll") for (int e = 0; e < 2; ++e)                           \
-        a0_[e] = (h4 ? q_[e] : p_[e]) + __shfl_xor_sync(DQA_FULL, h4 ? p_[e] : q_[e], 16); \
-    }                                                                         \
-    {                                                                         \
-      double p_[2], q_[2];                                                    \
-      D1(p_);                                                                 \
-      D3(q_);                                                                 \
-      _Pragma("unroll") for (int e = 0; e < 2; ++e)                           \
-        a1_[e] = (h4 ? q_[e] : p_[e]) + __shfl_xor_sync(DQA_FULL, h4 ? p_[e] : q_[e], 16); \
-    }                                                                         \
-    _Pragma("unroll") for (int e = 0; e < 2; ++e)                             \
-      out[e] = (h3 ? a1_[e] : a0_[e]) + __shfl_xor_sync(DQA_FULL, h3 ? a0_[e] : a1_[e], 8); \
-    _Pragma("unroll") for (int o = 4; o > 0; o >>= 1)                         \
-      _Pragma("unroll") for (int e = 0; e < 2; ++e) out[e] += __shfl_xor_sync(DQA_FULL, out[e], o); \
-  }
-#define JB_CROSS(J)                                                           \
-  {                                                                           \
-    double s_[2];                                                             \
-    _Pragma("diag_suppress 550")                                              \
-    auto D0 = [&](double (&o_)[2]) { JB_DOT(A[0], B[(0 + J) & 3], o_); };     \
-    auto D1 = [&](double (&o_)[2]) { JB_DOT(A[1], B[(1 + J) & 3], o_); };     \
-    auto D2 = [&](double (&o_)[2]) { JB_DOT(A[2], B[(2 + J) & 3], o_); };     \
-    auto D3 = [&](double (&o_)[2]) { JB_DOT(A[3], B[(3 + J) & 3], o_); };     \
-    JB_RS2(D0, D1, D2, D3, s_);                                               \
-    double c_ = 1.0;                                                          \
-    cplx z_ = cmk(0.0, 0.0);                                                  \
-    const int rot = jac_params(cmk(s_[0], s_[1]), nA, nB, tol2, quad2, c_, z_, mybig); \
-    JB_PUBLISH();                                                             \
-    if (fired) {                                                              \
-      JB_APPLY(0, A[0], B[(0 + J) & 3]);                                      \
-      JB_APPLY(1, A[1], B[(1 + J) & 3]);                                      \
-      JB_APPLY(2, A[2], B[(2 + J) & 3]);                                      \
-      JB_APPLY(3, A[3], B[(3 + J) & 3]);                                      \
-    }                                                                         \
-    nB = __shfl_sync(DQA_FULL, nB, (lane + 8) & 31);                          \
-  }
-// pairs inside the half-blocks: (A_a0, A_b0), (A_a1, A_b1), (B_a0, B_b0), (B_a1, B_b1); norms come with the dots
-#define JB_NRM(P, Q, acc)                                \
-  {                                                      \
-    double np_ = 0.0, nq_ = 0.0;                         \
-    _Pragma("unroll") for (int t = 0; t < RL; ++t) {     \
-      np_ += cabs2(P[t]);                                \
-      nq_ += cabs2(Q[t]);                                \
-    }                                                    \
-    acc[0] = np_;                                        \
-    acc[1] = nq_;                                        \
-  }
-#define JB_INTRA(a0, b0, a1, b1)                                              \
-  {                                                                           \
-    double v_[4][2], s_[2], n_[2];                                            \
-    JB_NRM(A[a0], A[b0], v_[0]);                                              \
-    JB_NRM(A[a1], A[b1], v_[1]);                                              \
-    JB_NRM(B[a0], B[b0], v_[2]);                                              \
-    JB_NRM(B[a1], B[b1], v_[3]);                                              \
-    warp_reduce_scatter4<2>(v_, n_, lane);                                    \
-    JB_DOT(A[a0], A[b0], v_[0]);                                              \
-    JB_DOT(A[a1], A[b1], v_[1]);                                              \
-    JB_DOT(B[a0], B[b0], v_[2]);                                              \
-    JB_DOT(B[a1], B[b1], v_[3]);                                              \
-    warp_reduce_scatter4<2>(v_, s_, lane);                                    \
-    double c_ = 1.0;                                                          \
-    cplx z_ = cmk(0.0, 0.0);                                                  \
-    const int rot = jac_params(cmk(s_[0], s_[1]), n_[0], n_[1], tol2, quad2, c_, z_, mybig); \
-    JB_PUBLISH();                                                             \
-    if (fired) {                                                              \
-      JB_APPLY(0, A[a0], A[b0]);                                              \
-      JB_APPLY(1, A[a1], A[b1]);                                              \
-      JB_APPLY(2, B[a0], B[b0]);                                              \
-      JB_APPLY(3, B[a1], B[b1]);                                              \
-    }                                                                         \
-  }
-
-  for (int sweep = 0; sweep < d.max_sweeps && !converged; ++sweep) {
-    if (tid == 0) {
-      sh_i[0] = 0;
-      sh_i[2] = 0;
-    }
-    int myrot = 0, mybig = 0;
-    double nA = 0.0, nB = 0.0;
-    if (act) {
-      JB_INTRA(0, 1, 2, 3);
-      JB_INTRA(0, 2, 1, 3);
-      JB_INTRA(0, 3, 1, 2);
-      // exact squared norms once per sweep: group kk gets |A_kk|^2, |B_kk|^2
-      double v_[4][2], s_[2];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        double na_ = 0.0, nb_ = 0.0;
-#pragma unroll
-        for (int t = 0; t < RL; ++t) {
-          na_ += cabs2(A[i][t]);
-          nb_ += cabs2(B[i][t]);
-        }
-        v_[i][0] = na_;
-        v_[i][1] = nb_;
-      }
-      warp_reduce_scatter4<2>(v_, s_, lane);
-      nA = s_[0];
-      nB = s_[1];
-    }
-    for (int round = 0; round < 2 * h; ++round) {
-      const bool straddle = round & 1;
-      if (act) {
-        if (straddle && w == 0) {  // both end half-blocks of the line: exchange roles, no rotation
-#pragma unroll
-          for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int t = 0; t < RL; ++t) {
-              const cplx t_ = A[i][t];
-              A[i][t] = B[i][t];
-              B[i][t] = t_;
-            }
-          const double tn = nA;
-          nA = nB;
-          nB = tn;
-        } else {
-          JB_CROSS(0);
-          JB_CROSS(1);
-          JB_CROSS(2);
-          JB_CROSS(3);
-        }
-      }
-      // ---- pass one half-block on: B to the right after an even block-round, A back to the left after an odd one ----
-      // (rows >= mr are zero in the registers and padded in the slots: no row guards, static offsets)
-      cplx* xb = X + (straddle ? bufsz : 0) + lane;
-      double* xnb = xn + (straddle ? 4 * h : 0);
-      if (!straddle) {
-        if (act) {
-          cplx* dst = xb + gr * 4 * MRC;
-#pragma unroll
-          for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int t = 0; t < RL; ++t) dst[i * MRC + 32 * t] = B[i][t];
-          if (li == 0) xnb[gr * 4 + kk] = nB;
-        }
-        __syncthreads();
-        if (act) {
-          const cplx* src = xb + w * 4 * MRC;
-#pragma unroll
-          for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int t = 0; t < RL; ++t) B[i][t] = src[i * MRC + 32 * t];
-          nB = xnb[w * 4 + kk];
-        }
-      } else {
-        if (act) {
-          cplx* dst = xb + gl * 4 * MRC;
-#pragma unroll
-          for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int t = 0; t < RL; ++t) dst[i * MRC + 32 * t] = A[i][t];
-          if (li == 0) xnb[gl * 4 + kk] = nA;
-        }
-        __syncthreads();
-        if (act) {
-          const cplx* src = xb + w * 4 * MRC;
-#pragma unroll
-          for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int t = 0; t < RL; ++t) A[i][t] = src[i * MRC + 32 * t];
-          nA = xnb[w * 4 + kk];
-        }
-      }
-    }
-    if (myrot) atomicAdd(&sh_i[0], myrot);
-    if (mybig) atomicOr(&sh_i[2], 1);
-    __syncthreads();
-    sweeps++;
-    nrot_total += (unsigned long long)sh_i[0];
-    converged = (sh_i[0] == 0) || (sh_i[2] == 0);  // same rule as k_jacobi
-    __syncthreads();
-  }
-#undef JB_DOT
-#undef JB_NRM
-#undef JB_APPLY
-#undef JB_PUBLISH
-#undef JB_CROSS
-#undef JB_RS2
-#undef JB_INTRA
-  // ---- park the columns in shared memory (MRC x kc, any order: the tail sorts by singular value) ----
-  __syncthreads();
-  if (act) {
-    cplx* dst = X + (size_t)(8 * w) * MRC + lane;
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-      for (int t = 0; t < RL; ++t) {
-        dst[i * MRC + 32 * t] = A[i][t];
-        dst[(4 + i) * MRC + 32 * t] = B[i][t];
-      }
-  }
-  __syncthreads();
-  jacobi_tail(jac_tail_args(d), inst, l, mu, p_step, X, MRC, mr, k, kc, sig, ssorted, order, sh_i, bond, converged, sweeps, nrot_total);
-}
-
-#ifndef JBLK_MINB2
-#define JBLK_MINB2 2  // CTAs per SM the two-rows-per-lane build (32 < 2chi <= 64) is compiled for
-#endif
-template <int RL>
-__global__ void __launch_bounds__(RL == 1 ? 128 : 256, RL == 1 ? 6 : JBLK_MINB2) k_jacobi_blk(DqaDev d, int l, int mu, int p_step) {
-  jacobi_blk_body<RL>(d, l, mu, p_step);
-}
+// Measured and rejected (round 2, commit bdc5484 has the kernel): k_jacobi_blk, the same SVD with the columns laid out
+// ROW-PER-LANE -- a warp owns 8 columns (two half-blocks of 4) for a whole block-round, a rotation of two of its columns
+// is lane-local, the 4 pair dots of a sub-round are summed by a reduce-scatter butterfly (12 double shuffles) that leaves
+// pair k in lanes 8k..8k+7, which compute the 4 parameter sets SIMT-parallel and publish them through 32 bytes of
+// warp-private shared memory; only every 4th sub-round a half-block crosses shared memory behind a block barrier (odd-even
+// transposition over half-blocks; 13 % fewer sweeps than the column ordering on the L factors of a chi=32 run).  Parity-green
+// on the GPU (37 teacher-forced sub-steps), and SLOWER at every bond: chi=32 481 vs 418 ms per step, chi=24 324 vs 210,
+// chi=16 98 vs 82, chi=10 62 vs 41 (batch 888).  Three of four barriers and exchanges are gone, but the two extra butterfly
+// stages, the operand selects of the reduce-scatter and the parameter broadcast put as much latency back into every
+// sub-round as the exchange took out of it, at 128 registers with spills (155 without the cap): the round is a latency
+// chain (dot -> reduce -> two dependent rsqrt -> rotate), and the layout does not shorten it.
 
 #ifndef DQA_EMUL
 // ---------------------------------------------------------------------------------

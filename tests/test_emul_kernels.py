@@ -47,6 +47,13 @@ def test_batch(factory):
     ps.check_batch_consistency(factory, "n7_chi4", steps=1, batch=3)
 
 
+def test_batch_split_into_sub_batches(factory, monkeypatch):
+    # DQA_SPLIT: the step runs the batch as independent sub-batches (views of the plan's buffers: 1 + 2 and 1 + 1 + 1 instances)
+    for ns in ("2", "3"):
+        monkeypatch.setenv("DQA_SPLIT", ns)
+        ps.check_batch_consistency(factory, "n7_chi4", steps=2, batch=3)
+
+
 def test_small_edge_cases(factory):
     ps.check_small_edge_cases(factory)
 

@@ -485,6 +485,41 @@ def test_step_graph_replay_equals_plain_launches(monkeypatch):
     assert np.array_equal(res["1"], res["0"])
 
 
+def test_sub_batches_on_parallel_graph_branches(monkeypatch):
+    """DQA_SPLIT: the captured step runs the batch as independent sub-batches on parallel branches of the graph (views of
+    the plan's buffers on the handle's own streams), the plain-launch path does the same with stream events.  Every
+    instance sees the same kernels with the same arguments as in an unsplit plan: traces, bond monitor, Schmidt values and
+    the states themselves must be identical to the bit, for uneven splits too, and the getters that follow a step (on the
+    handle's stream) must see the joined result."""
+    from perceptron_dqa_b200._lib import Plan
+
+    g = golden("c1_n12_chi10")
+    xi = g["xi"]
+    rng = np.random.default_rng(3)
+    batch = 7
+    pats = np.stack([xi] + [(2 * rng.integers(0, 2, size=xi.shape) - 1).astype(np.int8) for _ in range(batch - 1)])
+    out = {}
+    for split, graph in (("1", "1"), ("2", "1"), ("3", "1"), ("4", "0")):
+        monkeypatch.setenv("DQA_SPLIT", split)
+        monkeypatch.setenv("DQA_GRAPH", graph)
+        pl = Plan(xi.shape[1], xi.shape[0], int(g["P"]), float(g["dt"]), int(g["chi"]), batch=batch)
+        pl.set_patterns(pats)
+        pl.set_fourier(g["Uk_FT"], g["fxft"])
+        pl.reset_plus()
+        pl.step(3)
+        pl.step_async(2)
+        out[split] = (pl.eps_trace().copy(), pl.bd_monitor().copy(), [pl.schmidt(5, inst=i) for i in range(batch)],
+                      [np.concatenate([t.ravel() for t in pl.get_mps(i)]) for i in (0, 3, 6)], pl.status().copy())
+        pl.close()
+    ref = out["1"]
+    assert np.abs(ref[0][0, :6] - g["eps"][:6]).max() < 1e-10
+    for split in ("2", "3", "4"):
+        got = out[split]
+        assert np.array_equal(got[0], ref[0]) and np.array_equal(got[1], ref[1]) and np.array_equal(got[4], ref[4])
+        assert all(np.array_equal(a, b) for a, b in zip(got[2], ref[2]))
+        assert all(np.array_equal(a, b) for a, b in zip(got[3], ref[3]))
+
+
 def test_two_devices_in_one_process():
     """A handle is bound to its own device: plans on cuda:0 and cuda:1 stepped alternately from one thread give the
     single-device results, and the caller's current device is left alone (needs two GPUs; skipped otherwise)."""

@@ -786,6 +786,14 @@ __global__ void __launch_bounds__(1024) k_lq(DqaDev d, int l) {
   }
 }
 
+// Measured and rejected (round 2): ROW TEAMS in the panel factorisation -- the warps form R = pb-1-i teams of nwarp / R warps,
+// one team per remaining row, the row's columns split over the team's lanes, partial dots and partial norms meeting in shared
+// memory behind a named barrier of the team (bar.sync id, 32 T), every lane of the next reflector's team deriving the
+// scalars for itself -- so that all 16 warps work instead of at most 7 and the next reflector's warp no longer walks all n
+// columns three times.  Parity-green on the GPU, and SLOWER at every bond: LQ 221 vs 178 ms per step at chi=32 (panel phase
+// 223k vs 146k cycles per CTA), 87 vs 72 at chi=20, 41 vs 32 at chi=10, batch 888.  The extra warp reductions and barrier
+// traffic of 16 active warps cost more than the shorter critical path saves: with a second CTA on the SM in its DMMA phase the
+// panel phase is not waited for, it is paid for in issue slots.
 // Measured and rejected (round 2): the panel of k_lq held in REGISTERS, one column per thread (544 threads), with one
 // block-wide reduction per reflector (a 16-slot shuffle butterfly per warp for |x|^2 and the dots with all later panel
 // rows, one shared-memory hand-off, one barrier) and every thread deriving the reflector scalars for itself.  It removes

@@ -80,8 +80,9 @@ def ncu_summary(rep, kernel, tag):
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units, vals = rows[0], rows[1], rows[2]
     with open(os.path.join(PROF, f"{tag}_{kernel}_ncu_summary.csv"), "w") as f:
-        f.write(f"# {tag}: ncu --set full --clock-control none, {vals[hdr.index('Kernel Name')]}, 1 launch, batch 888, N=21, chi=32 "
-                f"(tools/profile_step.py --chi 32 --batch 888 --steps 1 --warmup 1)\n")
+        f.write(f"# {tag}: ncu --set full --clock-control none, {vals[hdr.index('Kernel Name')]}, 1 mid-chain launch, N=21, chi=32, plan of 888 "
+                f"realisations (tools/profile_step.py --chi 32 --batch 888; a grid of 296 instances = one of the three sub-batches the "
+                f"step graph launches, 888 = a whole-batch launch of the profiled step)\n")
         f.write("metric,unit,value\n")
         for key in NCU_KEEP:
             if key in hdr:

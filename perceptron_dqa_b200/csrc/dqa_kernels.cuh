@@ -786,7 +786,16 @@ __global__ void __launch_bounds__(1024) k_lq(DqaDev d, int l) {
   }
 }
 
-// Measured and rejected (round 2): ROW TEAMS in the panel factorisation -- the warps form R = pb-1-i teams of nwarp / R warps,
+// Measured and rejected (round 2; branch exp/lq-panel-pivot): PANEL-LEVEL PIVOTING -- every panel takes the 8 rows of largest
+// residual norm (norms
+// computed once, downdated by the L entries each trailing update produces; rows addressed through a position -> row map, the
+// Jacobi tail un-permuting the rows of the new site tensor), which grades the factor a la Drmac-Veselic without a second
+// factorisation.  Parity-green on the GPU; the Jacobi needs 6.08 instead of 6.51 sweeps per SVD (5 908 vs 6 414 rotations;
+// tools/jacobi_study.py PIVOT=1 predicts 7.8 vs 8.6 on the mid-chain factors) and takes 394 instead of 418 ms per step at
+// chi=32 -- and the LQ takes 192 instead of 178 ms (one more pass over Theta for the norms, a rank sort per panel, indirect
+// row addressing): 1.006 s per step against 1.005 s.  A wash; left out.
+// Measured and rejected (round 2; branch exp/lq-row-teams): ROW TEAMS in the panel factorisation -- the warps form R = pb-1-i
+// teams of nwarp / R warps,
 // one team per remaining row, the row's columns split over the team's lanes, partial dots and partial norms meeting in shared
 // memory behind a named barrier of the team (bar.sync id, 32 T), every lane of the next reflector's team deriving the
 // scalars for itself -- so that all 16 warps work instead of at most 7 and the next reflector's warp no longer walks all n
@@ -1371,7 +1380,8 @@ __global__ void __launch_bounds__(RS * 32, RS > 8 ? 1 : (RS == 8 ? JSYS_MINB8 : 
 
 
 
-// Measured and rejected (round 2, commit bdc5484 has the kernel): k_jacobi_blk, the same SVD with the columns laid out
+// Measured and rejected (round 2; commit bdc5484, branch exp/jacobi-row-per-lane): k_jacobi_blk, the same SVD with the columns
+// laid out
 // ROW-PER-LANE -- a warp owns 8 columns (two half-blocks of 4) for a whole block-round, a rotation of two of its columns
 // is lane-local, the 4 pair dots of a sub-round are summed by a reduce-scatter butterfly (12 double shuffles) that leaves
 // pair k in lanes 8k..8k+7, which compute the 4 parameter sets SIMT-parallel and publish them through 32 bytes of

@@ -299,3 +299,43 @@ def ordering_study():
 
 if __name__ == "__main__" and os.environ.get("ORDERING"):
     ordering_study()
+
+
+def panel_pivot_lq(th, pb=8):
+    """L of an LQ whose next panel is always the pb rows of largest residual norm (the k_lq variant measured in round 2):
+    returns the row-permuted, lower-triangular factor."""
+    m = th.shape[0]
+    R = th.copy()  # residual rows: orthogonal complement of the directions chosen so far
+    rem, order, qrows = list(range(m)), [], []
+    while rem:
+        nr = np.linalg.norm(R[rem], axis=1)
+        for j in [rem[i] for i in np.argsort(-nr, kind="stable")[:pb]]:
+            q = R[j] / max(np.linalg.norm(R[j]), 1e-300)
+            qrows.append(q)
+            rem.remove(j)
+            order.append(j)
+            for r in rem:
+                R[r] = R[r] - (R[r] @ q.conj()) * q
+    return th[order] @ np.array(qrows).conj().T
+
+
+def pivot_study():
+    """PIVOT=1: sweeps of the kernel's Jacobi on L from the natural-order LQ, from rows sorted once, from panel-level pivoting
+    and from full row pivoting, on mid-chain factors of a warm chi=32 run."""
+    import scipy.linalg as sl
+    mats = collect(32, warm_patterns=40, want=24)
+    oe = oddeven_rounds(64)
+
+    def rep(name, fn):
+        out = [scalar_jacobi(fn(th), oe) for th in mats]
+        print(f"{name:52s} sweeps {np.mean([o[1] for o in out]):5.2f} rot {np.mean([o[2] for o in out]):8.1f} active_rounds {np.mean([o[3] for o in out]):.0f}")
+
+    rep("LQ in the natural row order (k_lq)", lq_l)
+    rep("rows sorted once by norm, then LQ", lambda th: lq_l(th[np.argsort(-np.linalg.norm(th, axis=1))]))
+    rep("panel-level pivoting, panels of 8", lambda th: panel_pivot_lq(th, 8))
+    rep("panel-level pivoting, panels of 16", lambda th: panel_pivot_lq(th, 16))
+    rep("full row pivoting (QRCP of Theta^H)", lambda th: sl.qr(th.conj().T, mode='economic', pivoting=True)[1].conj().T.copy())
+
+
+if __name__ == "__main__" and os.environ.get("PIVOT"):
+    pivot_study()

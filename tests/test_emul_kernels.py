@@ -54,6 +54,38 @@ def test_batch_split_into_sub_batches(factory, monkeypatch):
         ps.check_batch_consistency(factory, "n7_chi4", steps=2, batch=3)
 
 
+def test_batch_split_with_per_instance_dt(monkeypatch):
+    # the views of a split plan carry the per-instance table index and dt: two instances with different dt, one per sub-batch
+    import numpy as np
+
+    import dqa_oracle as O
+    import emul_lib
+    from helpers import golden
+    from perceptron_dqa_b200._lib import Plan
+
+    monkeypatch.setenv("DQA_SPLIT", "2")
+    kw = dict(lib=emul_lib.load(), workspace=emul_lib.numpy_workspace)
+    g = golden("n7_chi4")
+    xi, P, dt, chi = g["xi"], int(g["P"]), float(g["dt"]), int(g["chi"])
+    n, nx = xi.shape[1], xi.shape[0]
+    dts = [dt, 0.4]
+    uks = np.stack([O.fourier_tables(n, P, v)[0] for v in dts])
+    both = Plan(n, nx, P, dt, chi, batch=2, n_tables=2, **kw)
+    both.set_patterns(np.stack([xi, xi]))
+    both.set_fourier_tables(uks, g["fxft"], [0, 1], dts)
+    both.reset_plus()
+    both.step(2)
+    monkeypatch.setenv("DQA_SPLIT", "1")
+    for i, v in enumerate(dts):
+        one = Plan(n, nx, P, v, chi, **kw)
+        one.set_patterns(xi[None])
+        one.set_fourier(uks[i], g["fxft"])
+        one.reset_plus()
+        one.step(2)
+        assert np.abs(both.eps_trace()[i, :3] - one.eps_trace()[0, :3]).max() < 1e-13
+    assert np.abs(both.eps_trace()[0, :3] - g["eps"][:3]).max() < 1e-10
+
+
 def test_small_edge_cases(factory):
     ps.check_small_edge_cases(factory)
 

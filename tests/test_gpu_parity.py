@@ -518,6 +518,20 @@ def test_sub_batches_on_parallel_graph_branches(monkeypatch):
         assert np.array_equal(got[0], ref[0]) and np.array_equal(got[1], ref[1]) and np.array_equal(got[4], ref[4])
         assert all(np.array_equal(a, b) for a, b in zip(got[2], ref[2]))
         assert all(np.array_equal(a, b) for a, b in zip(got[3], ref[3]))
+    # instances with different dt (per-instance Fourier tables) land in different sub-batches
+    g7 = golden("n7_chi4")
+    res = {}
+    for split in ("1", "2"):
+        monkeypatch.setenv("DQA_SPLIT", split)
+        monkeypatch.setenv("DQA_GRAPH", "1")
+        from perceptron_dqa_b200.dQA_mps import mydQA
+
+        obj = mydQA(np.stack([g7["xi"]] * 4), P=int(g7["P"]), dt=[float(g7["dt"]), 0.4, 0.4, float(g7["dt"])], max_bond=int(g7["chi"]))
+        obj.init_fourier()
+        obj.run(print_info=False)
+        res[split] = obj.eps.copy()
+    assert np.array_equal(res["1"], res["2"])
+    assert np.abs(res["2"][0][:4] - g7["eps"][:4]).max() < 1e-10 and np.array_equal(res["2"][0], res["2"][3])
 
 
 def test_two_devices_in_one_process():

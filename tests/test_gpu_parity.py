@@ -534,6 +534,31 @@ def test_sub_batches_on_parallel_graph_branches(monkeypatch):
     assert np.abs(res["2"][0][:4] - g7["eps"][:4]).max() < 1e-10 and np.array_equal(res["2"][0], res["2"][3])
 
 
+def test_sub_batches_with_the_big_bond_kernels(monkeypatch):
+    """The same bit-for-bit statement for the kernels of bonds above 32 (cluster Jacobi at chi=64, one-CTA systolic Jacobi at
+    chi=48, 12- and 16-slot sector QR), N=21, two saturating steps of 150 realisations in sub-batches of 75."""
+    from perceptron_dqa_b200._lib import Plan
+
+    N, nxi, P, dt = 21, 17, 1000, 1.0
+    uk, fx = O.fourier_tables(N, P, dt)
+    for chi, batch in ((64, 150), (48, 150)):
+        rng = np.random.default_rng(chi)
+        xi = (2 * rng.integers(0, 2, size=(batch, nxi, N)) - 1).astype(np.int8)
+        out = {}
+        for ns in ("1", "2"):
+            monkeypatch.setenv("DQA_SPLIT", ns)
+            pl = Plan(N, nxi, P, dt, chi, batch=batch)
+            pl.set_patterns(xi)
+            pl.set_fourier(uk, fx)
+            pl.reset_plus()
+            pl.pp = P // 2
+            pl.step(2)
+            out[ns] = (pl.eps_trace()[:, P // 2: P // 2 + 3].copy(), pl.status().copy(), pl.bd_monitor().copy())
+            pl.close()
+        assert np.array_equal(out["1"][0], out["2"][0]) and np.array_equal(out["1"][2], out["2"][2])
+        assert not out["2"][1].any()
+
+
 def test_two_devices_in_one_process():
     """A handle is bound to its own device: plans on cuda:0 and cuda:1 stepped alternately from one thread give the
     single-device results, and the caller's current device is left alone (needs two GPUs; skipped otherwise)."""

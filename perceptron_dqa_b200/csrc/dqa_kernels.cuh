@@ -467,6 +467,13 @@ __device__ __forceinline__ void theta_gemm2(cplx* thc, int ld, int offo, int s, 
 // fragment loads per 16 DMMAs instead of 3 per 8, aimed at the 82 % busy L1 data pipe).  98 registers instead of 56 cut the
 // resident CTAs per SM from 9 to 5 and the kernel got SLOWER: 92.6 vs 71.6 ms per step at chi=32, 107.6 vs 76.4 at chi=48
 // (batch 888 / 296).  The loads from global memory are hidden by warps in flight, not by fewer loads.
+// Measured and rejected (round 2; branch exp/theta-bulk-staging): k_theta_bulk -- all three operands staged in shared memory by
+// the TMA engine (cp.async.bulk: one copy for the site tensor, one for the Q block, one per row of the Theta block; two
+// mbarriers counting bytes; UBLKCP / SYNCS in the SASS, 58 registers), GEMM-1 accumulators held in registers across a barrier so
+// that C takes the Theta block's place, every DMMA fragment read from shared memory with conflict-free strides.  Parity-green
+// on the GPU, and SLOWER: 113 ms per step with 128-thread CTAs, 103 ms with 256, against 73 ms at chi=32 (45 vs 38 at chi=20,
+// equal at chi=10; batch 888).  96 KB of operands leave two CTAs per SM instead of nine; nine CTAs' worth of warps hide the
+// L2 latency of the direct fragment loads better than two CTAs hide their staging phase.
 // row stride of C in shared memory: = 4 (mod 8) complex, so the two rows a quarter-warp reads in one DMMA fragment load
 // (4 consecutive k each) do not share banks
 __host__ __device__ inline int theta_ldc(int chi) { return ((chi + 7) & ~7) + 4; }

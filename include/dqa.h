@@ -16,7 +16,9 @@
  *  - complex128 is interleaved (re, im) doubles, the numpy layout.  MPS site tensors cross
  *    the ABI in the reference's (l, phys=2, r) row-major layout (lib/tenn.py:72-75).
  *  - A handle is bound to one device and one stream and is not thread-safe; calls are
- *    stream-ordered, the get/energy calls synchronise the stream.
+ *    stream-ordered, the get/energy calls synchronise the stream.  dqa_step() may fan the
+ *    batch out over streams of its own (sub-batches on parallel branches of the step graph);
+ *    they are joined into the handle's stream before the step counts as done there.
  *  - There is no CPU fallback anywhere behind this ABI.
  */
 #ifndef DQA_H_
